@@ -1,0 +1,124 @@
+/*
+ * gmpi_mpi_render.h -- C ABI of the B200 (sm_100a) multiplane-image renderer.
+ *
+ * Drop-in boundary for ONE path of apple/ml-gmpi: the over-composite render of
+ * gmpi/core/mpi.py (MPI.forward :308-436 + homography :26-153) as driven by
+ * MPIRenderer.render (gmpi/core/mpi_renderer.py:387-469).  The reference has no FFI for this
+ * path (it is a chain of ~30 ATen kernels); these entry points are what a binding for it binds.
+ * INTEGRATION.md shows the ctypes stub and the two-line patch on the reference side.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch types.  All tensors fp32, contiguous,
+ *     row-major, on the CUDA device that is current on the calling thread (except *_host).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All device
+ *     entry points are asynchronous on that stream and allocate nothing.
+ *   - return value: GMPI_OK, or an error code with a message available from gmpi_last_error()
+ *     (thread-local).  The library never exits the process (the reference calls sys.exit(1) when
+ *     rays leave the last plane, mpi.py:122-128; here that is a flag bit).
+ *
+ * Layouts (names follow the reference)
+ *   rgba      [M, N, 4, Ht, Wt]  MPI textures in [0,1], planes ordered near -> far (mpi.py:413)
+ *   dhw       [M, N, 3]          per plane: distance, metric height, metric width (mpi.py:59-63)
+ *   view2mpi  [V] int32          MPI index of every rendered view.  Replaces the expand+cat of
+ *                                mpi.py:334-346 (no copy of the MPI per view); views are
+ *                                MPI-major like the reference's concatenation.
+ *   ray_dir   [V, 3, H, W]       world-space unit rays per pixel (camera.py:182-211)
+ *   eye       [V, 3]             camera position (camera.py:189)
+ *   z_dir     [V, 3]             optical axis (camera.py:209)
+ *   color     [V, 3, H, W]       composited colour in [0,1] (or 2c-1 if GMPI_COLOR_MINUS1_1)
+ *   depth     [V, 1, H, W]       transmittance-weighted z-depth (mpi.py:434)
+ *   flags     [1] uint32         OR-ed GMPI_FLAG_* bits (device memory; caller zeroes it)
+ */
+#ifndef GMPI_MPI_RENDER_H_
+#define GMPI_MPI_RENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMPI_ABI_VERSION 1
+
+/* return codes */
+#define GMPI_OK 0
+#define GMPI_ERR_INVALID_ARGUMENT 1
+#define GMPI_ERR_CUDA 2
+#define GMPI_ERR_UNSUPPORTED 3
+
+/* flag bits written to *flags: the reference's data-dependent asserts, reported instead of raised */
+#define GMPI_FLAG_RGBA_RANGE 1u        /* rgba outside [0,1]            mpi_renderer.py:447-449 */
+#define GMPI_FLAG_ALPHA_RANGE 2u       /* alpha outside [0,1]           mpi.py:185-187          */
+#define GMPI_FLAG_LAST_PLANE_OOB 4u    /* |u| or |v| > 1 on last plane  mpi.py:103-109,381-395  */
+#define GMPI_FLAG_PLANE_BEHIND_EYE 8u  /* distance < z_eye[0]           mpi.py:70-72            */
+
+/* option bits for `options` */
+#define GMPI_ALIGN_CORNERS 1u          /* MPI(align_corners=True), configs/gmpi.yml:74          */
+#define GMPI_CHECK_LAST_PLANE 2u       /* assert_not_out_of_last_plane, mpi.py:317              */
+#define GMPI_COLOR_MINUS1_1 4u         /* fuse "2*color-1" of mpi_renderer.py:467 into the store */
+#define GMPI_ZERO_GRAD 8u              /* bwd: zero g_rgba on the stream before accumulating    */
+
+int gmpi_abi_version(void);
+const char* gmpi_last_error(void);
+
+/* Name of the kernel variant a forward call with these shapes would launch (diagnostics). */
+const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W);
+
+/*
+ * Forward: replaces MPI.forward (mpi.py:308-436) for all V views in one launch.
+ * Per output pixel the planes are walked front to back; colour, depth and transmittance stay in
+ * registers; no [V*N, c, H, W] intermediate is written.
+ */
+int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                        const float* ray_dir, const float* eye, const float* z_dir,
+                        float* color, float* depth, uint32_t* flags,
+                        int M, int V, int N, int Ht, int Wt, int H, int W,
+                        uint32_t options, void* stream);
+
+/*
+ * Backward: d(sum(color*g_color) + sum(depth*g_depth)) / d rgba, what torch autograd produces for
+ * MPI.forward (only the sampled rgba carries gradient: mpi.py:65,148 run under no_grad).
+ * g_depth may be NULL.  Views of one MPI accumulate into the same g_rgba slab (the `expand` of
+ * train.py:733-738).  g_rgba must be zero, or pass GMPI_ZERO_GRAD.
+ * If options has GMPI_COLOR_MINUS1_1 the upstream g_color is w.r.t. 2*color-1.
+ */
+int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                        const float* ray_dir, const float* eye, const float* z_dir,
+                        const float* g_color, const float* g_depth, float* g_rgba,
+                        int M, int V, int N, int Ht, int Wt, int H, int W,
+                        uint32_t options, void* stream);
+
+/*
+ * Range checks of MPIRenderer.render (mpi_renderer.py:447-449) and MPI.check_shapes
+ * (mpi.py:185-187) in one streaming pass: sets GMPI_FLAG_RGBA_RANGE / GMPI_FLAG_ALPHA_RANGE.
+ */
+int gmpi_mpi_check_range(const float* rgba, int M, int N, int Ht, int Wt, uint32_t* flags,
+                         void* stream);
+
+/*
+ * Host-buffer forward (end-to-end entry point): all pointers are HOST memory (pinned memory
+ * overlaps best).  Copies inputs to `device`, renders, copies colour/depth/flags back and
+ * synchronises.  MPIs are streamed through a double-buffered device staging area so the copy of
+ * MPI m+1 overlaps the render of MPI m.  *flags_out receives the OR of all flag bits.
+ */
+int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                             const float* ray_dir, const float* eye, const float* z_dir,
+                             float* color, float* depth, uint32_t* flags_out,
+                             int M, int V, int N, int Ht, int Wt, int H, int W,
+                             uint32_t options, int device);
+
+/* Test hook: texel coordinates (ix, iy) of every (view, plane, pixel), out [V,N,2,H,W]; the
+ * bit-exact stage of the path (must equal torch's fp32 op sequence, DESIGN.md "coordinates"). */
+int gmpi_debug_plane_coords(const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                            const float* eye, float* out, int V, int N, int Ht, int Wt, int H,
+                            int W, uint32_t options, void* stream);
+
+/* Test hook: out_fast[i] = the kernels' reciprocal+FMA division a[i]/b[i]; out_ieee[i] = div.rn.f32. */
+int gmpi_debug_division(const float* a, const float* b, float* out_fast, float* out_ieee, size_t n,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMPI_MPI_RENDER_H_ */

@@ -1,0 +1,70 @@
+"""ctypes binding of the C ABI in include/gmpi_mpi_render.h.
+
+There is no CPU or PyTorch fallback: if the library is missing or fails to load this raises."""
+import ctypes
+import os
+
+from ._build import LIB_PATH
+
+GMPI_OK = 0
+FLAG_RGBA_RANGE = 1
+FLAG_ALPHA_RANGE = 2
+FLAG_LAST_PLANE_OOB = 4
+FLAG_PLANE_BEHIND_EYE = 8
+
+OPT_ALIGN_CORNERS = 1
+OPT_CHECK_LAST_PLANE = 2
+OPT_COLOR_MINUS1_1 = 4
+OPT_ZERO_GRAD = 8
+
+ABI_VERSION = 1
+
+EXPORTS = [
+    "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
+    "gmpi_mpi_render_bwd", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_debug_plane_coords", "gmpi_debug_division",
+]
+
+_lib = None
+
+
+class GmpiLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GmpiLibraryError(
+            f"{LIB_PATH} is missing: the CUDA (sm_100a) renderer is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32
+    lib.gmpi_abi_version.restype = i
+    lib.gmpi_abi_version.argtypes = []
+    lib.gmpi_last_error.restype = ctypes.c_char_p
+    lib.gmpi_last_error.argtypes = []
+    lib.gmpi_mpi_render_fwd_variant.restype = ctypes.c_char_p
+    lib.gmpi_mpi_render_fwd_variant.argtypes = [i] * 5
+    lib.gmpi_mpi_render_fwd.restype = i
+    lib.gmpi_mpi_render_fwd.argtypes = [vp] * 9 + [i] * 7 + [u32, vp]
+    lib.gmpi_mpi_render_bwd.restype = i
+    lib.gmpi_mpi_render_bwd.argtypes = [vp] * 9 + [i] * 7 + [u32, vp]
+    lib.gmpi_mpi_check_range.restype = i
+    lib.gmpi_mpi_check_range.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.gmpi_mpi_render_fwd_host.restype = i
+    lib.gmpi_mpi_render_fwd_host.argtypes = [vp] * 9 + [i] * 7 + [u32, i]
+    lib.gmpi_debug_plane_coords.restype = i
+    lib.gmpi_debug_plane_coords.argtypes = [vp] * 5 + [i] * 6 + [u32, vp]
+    lib.gmpi_debug_division.restype = i
+    lib.gmpi_debug_division.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, vp]
+    if lib.gmpi_abi_version() != ABI_VERSION:
+        raise GmpiLibraryError(f"ABI mismatch: library {lib.gmpi_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != GMPI_OK:
+        raise GmpiLibraryError(f"gmpi error {rc}: {load().gmpi_last_error().decode()}")

@@ -1,0 +1,115 @@
+"""Pinhole camera rays and sphere-orbit poses: the small per-view inputs of the render path.
+
+Mirrors, re-derived rather than transcribed:
+  Camera / gen_cam            gmpi/core/camera.py:13-211, gmpi/utils/cam_utils.py:16-22
+  gen_sphere_path + helpers   gmpi/utils/cam_utils.py:481-622,687-821
+  MPIRenderer.sample_cam_poses / view_info_from_c2w_mat   gmpi/core/mpi_renderer.py:320-385
+
+Conventions (reference): world/MPI frame +X right, +Y down, +Z forward; the camera sits on a sphere
+(centre `sphere_center`, radius r) and looks at the centre; yaw moves it horizontally, pitch
+vertically; pixel centres at (+0.5, +0.5); principal point (w/2, h/2); f = w / (2 tan(fov/2)).
+"""
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+
+def focal_from_fov(fov_deg: float, width: int) -> float:
+    return width / (2.0 * math.tan(math.pi * fov_deg / 360.0))          # mpi_renderer.py:88-89
+
+
+class PinholeCamera:
+    """Per-pixel unit rays in camera space (fp64 -> fp32, cached), rotated to world space per view."""
+
+    def __init__(self, height: int, width: int, focal: float, ray_from_pix_center: bool = True):
+        self.height, self.width, self.focal = int(height), int(width), float(focal)
+        self.ray_from_pix_center = ray_from_pix_center
+        self._rays = {}
+
+    @classmethod
+    def from_fov(cls, fov_deg: float, height: int, width: int):
+        return cls(height, width, focal_from_fov(fov_deg, width))
+
+    def _cam_dirs64(self) -> np.ndarray:
+        off = 0.5 if self.ray_from_pix_center else 0.0                   # camera.py:63-66
+        xs = (np.arange(self.width, dtype=np.float64) + off - self.width / 2.0) / self.focal
+        ys = (np.arange(self.height, dtype=np.float64) + off - self.height / 2.0) / self.focal
+        d = np.stack(np.broadcast_arrays(xs[None, :], ys[:, None], np.ones((1, 1))), 0)     # K^-1 [u v 1]
+        return (d / np.linalg.norm(d, axis=0, keepdims=True)).reshape(3, -1)               # camera.py:98-105
+
+    def border_dirs64(self) -> np.ndarray:
+        """Unit rays through the four image corners (camera.py:79-96,107-114): [3,4]."""
+        t = np.array([[-1, 1, -1, 1], [-1, -1, 1, 1]], np.float64)
+        d = np.stack([t[0] * self.width / 2.0 / self.focal, t[1] * self.height / 2.0 / self.focal, np.ones(4)])
+        return d / np.linalg.norm(d, axis=0, keepdims=True)
+
+    def cam_dirs(self, device) -> torch.Tensor:
+        key = str(device)
+        if key not in self._rays:
+            self._rays[key] = torch.from_numpy(self._cam_dirs64()).float().to(device)      # camera.py:116-130
+        return self._rays[key]
+
+    def generate_rays(self, c2w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """c2w [V,4,4] fp32 -> ray_dir [V,3,H,W], eye [V,3], z_dir [V,3] (camera.py:182-211, batched)."""
+        rot = c2w[:, :3, :3]
+        rays = torch.matmul(rot, self.cam_dirs(c2w.device)).reshape(-1, 3, self.height, self.width)
+        return rays.contiguous(), c2w[:, :3, 3].contiguous(), rot[:, :, 2].contiguous()
+
+
+def truncated_normal(n: int, mean: float, std: float, n_std: float, generator: Optional[torch.Generator] = None):
+    """Draw 4 normals per sample and keep the first inside mean +- n_std*std (gmpi/utils/torch_utils.py:51-76)."""
+    tmp = torch.randn((n, 1, 4), generator=generator) * std + mean
+    lo, hi = mean - n_std * std, mean + n_std * std
+    ok = (tmp < hi) & (tmp > lo)
+    first = ok.float().argmax(-1, keepdim=True)
+    return tmp.gather(-1, first).squeeze(-1).clamp(lo, hi)
+
+
+def sphere_poses(yaws: torch.Tensor, pitches: torch.Tensor, sphere_center, sphere_r: float = 1.0) -> torch.Tensor:
+    """Camera-to-world matrices [V,4,4] (fp32 values) for cameras on the sphere looking at its centre.
+
+    Sphere frame (+X back, +Y right, +Z up): p = r(|cos pitch| cos yaw, |cos pitch| sin yaw, sin pitch)
+    (cam_utils.py:561-564); forward = -p/|p|; right = down0 x forward with down0 = (0,0,-1); down = forward x
+    right (cam_utils.py:571-622).  Sphere -> world maps (x,y,z) to (y,-z,-x) + centre, i.e. Rx(90deg) Rz(-90deg)
+    then the translation (cam_utils.py:687-731)."""
+    yaws = yaws.reshape(-1, 1).float()
+    pitches = pitches.reshape(-1, 1).float()
+    cp = torch.abs(torch.cos(pitches))
+    pos = sphere_r * torch.cat([cp * torch.cos(yaws), cp * torch.sin(yaws), torch.sin(pitches)], 1)     # fp32, like the reference
+    unit = lambda v: v / torch.norm(v, dim=-1, keepdim=True)
+    fwd = unit(-pos)
+    down0 = torch.tensor([0.0, 0.0, -1.0]).expand_as(fwd)
+    right = unit(torch.cross(down0, fwd, dim=-1))
+    down = unit(torch.cross(fwd, right, dim=-1))
+    c2s = torch.eye(4).repeat(pos.shape[0], 1, 1)
+    c2s[:, :3, :3] = torch.stack((right, down, fwd), dim=-1)
+    c2s[:, :3, 3] = pos
+    s2w = np.array([[0, 1, 0, 0], [0, 0, -1, 0], [-1, 0, 0, 0], [0, 0, 0, 1]], np.float64)
+    s2w[:3, 3] = np.asarray(sphere_center, np.float64).reshape(-1)
+    return torch.from_numpy(np.matmul(s2w, c2s.numpy().astype(np.float64))).float()                    # cam_utils.py:798, :364
+
+
+def sample_yaw_pitch(n, h_mean, h_std, v_mean, v_std, n_std=2, method="truncated_gaussian", random_pose=True,
+                     horizontal_sweep=True, generator=None):
+    """Pose angles as sample_camera_positions_sphere draws them (cam_utils.py:510-555)."""
+    if random_pose:
+        if method == "uniform":
+            y = (torch.rand((n, 1), generator=generator) - 0.5) * 2 * n_std * h_std + h_mean
+            p = (torch.rand((n, 1), generator=generator) - 0.5) * 2 * n_std * v_std + v_mean
+        elif method in ("normal", "gaussian"):
+            y = torch.randn((n, 1), generator=generator) * h_std + h_mean
+            p = torch.randn((n, 1), generator=generator) * v_std + v_mean
+        elif method == "truncated_gaussian":
+            y = truncated_normal(n, h_mean, h_std, n_std, generator)
+            p = truncated_normal(n, v_mean, v_std, n_std, generator)
+        else:
+            raise ValueError(method)
+    elif horizontal_sweep:
+        y = torch.linspace(-n_std, n_std, n).reshape(n, 1) * h_std + h_mean
+        p = torch.ones((n, 1)) * v_mean
+    else:
+        y = torch.ones((n, 1)) * h_mean
+        p = torch.linspace(-n_std, n_std, n).reshape(n, 1) * v_std + v_mean
+    return y, p

@@ -1,0 +1,171 @@
+// Shared device helpers of the MPI render kernels (sm_100a).
+//
+// The coordinate stage reproduces, bit for bit, the fp32 operation sequence of the reference
+// (gmpi/core/mpi.py:74-90 + ATen grid_sampler_unnormalize) because the texel coordinate is
+// amplified by (texture size x texel gradient): see DESIGN.md "Coordinates".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gmpi {
+
+struct RenderParams {
+    const float* rgba;        // [M,N,4,Ht,Wt]
+    const int32_t* view2mpi;  // [V]
+    const float* dhw;         // [M,N,3]
+    const float* ray_dir;     // [V,3,H,W]
+    const float* eye;         // [V,3]
+    const float* z_dir;       // [V,3]
+    float* color;             // [V,3,H,W]
+    float* depth;             // [V,1,H,W]
+    uint32_t* flags;          // [1]
+    const float* g_color;     // bwd
+    const float* g_depth;     // bwd, nullable
+    float* g_rgba;            // bwd
+    int M, V, N, Ht, Wt, H, W;
+    uint32_t options;
+};
+
+// Per (view, plane) constants, staged in shared memory once per CTA.
+//   a = {z_diff, pw, ph, fast}   b = {rcp(pw), rcp(ph), -, -}
+// z_diff = d - e_z (mpi.py:74).  `fast` != 0 when the three divisors/dividends are in the
+// exponent range where the FMA-corrected reciprocal division below is provably IEEE-exact.
+struct PlaneConst {
+    float z_diff, pw, ph, fast;
+    float ypw, yph, pad0, pad1;
+};
+
+__device__ __forceinline__ bool in_safe_range(float x) {
+    const float ax = fabsf(x);
+    return ax >= 0x1p-40f && ax <= 0x1p40f;
+}
+
+// a / b, correctly rounded, given y = RN(1/b): q0 = RN(a*y); r = a - q0*b (exact in an FMA);
+// q = RN(q0 + r*y).  (Markstein's theorem; verified exhaustively over all divisor mantissas
+// on the CPU and against __fdiv_rn on the GPU by tests/test_gpu_coords.py.)
+__device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
+    const float q0 = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(r, y, q0);
+}
+
+__device__ __forceinline__ PlaneConst make_plane_const(const float* __restrict__ dhw_plane, float eye_z) {
+    PlaneConst c;
+    const float d = dhw_plane[0], ph = dhw_plane[1], pw = dhw_plane[2];
+    c.z_diff = __fsub_rn(d, eye_z);
+    c.pw = pw;
+    c.ph = ph;
+    c.ypw = __frcp_rn(pw);
+    c.yph = __frcp_rn(ph);
+    const bool ok = (c.z_diff == 0.0f || in_safe_range(c.z_diff)) && in_safe_range(pw) && in_safe_range(ph);
+    c.fast = ok ? 1.0f : 0.0f;
+    c.pad0 = c.pad1 = 0.0f;
+    return c;
+}
+
+// Per-pixel ray constants.
+struct RayConst {
+    float rx2, ry2;   // 2*ray_x, 2*ray_y  (exact scaling: RN(2a) = 2 RN(a))
+    float rz, yrz;    // ray_z and RN(1/ray_z)
+    float ex2, ey2;   // 2*eye_x, 2*eye_y
+    float dz;         // ray . z_dir   (mpi.py:149)
+    bool fast;
+};
+
+__device__ __forceinline__ RayConst make_ray_const(float rx, float ry, float rz, const float* e, const float* zd) {
+    RayConst r;
+    r.rx2 = 2.0f * rx;
+    r.ry2 = 2.0f * ry;
+    r.rz = rz;
+    r.yrz = __frcp_rn(rz);
+    r.ex2 = 2.0f * e[0];
+    r.ey2 = 2.0f * e[1];
+    r.dz = fmaf(rz, zd[2], fmaf(ry, zd[1], rx * zd[0]));
+    r.fast = in_safe_range(rz);
+    return r;
+}
+
+struct TexCoord {
+    float ix, iy, scale, u, v;
+};
+
+// mpi.py:74-99 + grid_sampler_unnormalize.  Every operation rounds exactly as the reference's
+// separate elementwise kernels do (no FMA contraction across reference ops).
+template <bool kAlignCorners>
+__device__ __forceinline__ TexCoord plane_coord(const PlaneConst& pc, const RayConst& rc, float hsx, float hsy,
+                                                float fWt, float fHt) {
+    TexCoord t;
+    float s, u, v;
+    if (pc.fast != 0.0f && rc.fast) {
+        s = div_by_rcp(pc.z_diff, rc.rz, rc.yrz);                       // scale = z_diff / ray_z   (:76)
+        const float X2 = __fadd_rn(rc.ex2, __fmul_rn(rc.rx2, s));      // 2*(e_x + ray_x*scale)    (:79,:90)
+        const float Y2 = __fadd_rn(rc.ey2, __fmul_rn(rc.ry2, s));
+        u = div_by_rcp(X2, pc.pw, pc.ypw);                             // u = 2x / width           (:90)
+        v = div_by_rcp(Y2, pc.ph, pc.yph);                             // v = 2y / height          (:89)
+    } else {
+        s = __fdiv_rn(pc.z_diff, rc.rz);
+        const float X2 = __fadd_rn(rc.ex2, __fmul_rn(rc.rx2, s));
+        const float Y2 = __fadd_rn(rc.ey2, __fmul_rn(rc.ry2, s));
+        u = __fdiv_rn(X2, pc.pw);
+        v = __fdiv_rn(Y2, pc.ph);
+    }
+    if (kAlignCorners) {
+        // ((u+1)/2)*(size-1) == (u+1)*((size-1)/2): the halving is exact, so both round the same
+        // real product (ATen's CPU kernel uses the second form, its CUDA kernel the first).
+        t.ix = __fmul_rn(__fadd_rn(u, 1.0f), hsx);
+        t.iy = __fmul_rn(__fadd_rn(v, 1.0f), hsy);
+    } else {
+        if (u >= -1.0f && u <= 1.0f) u = __fmul_rn(u, 0.95f);            // mpi.py:95-99
+        if (v >= -1.0f && v <= 1.0f) v = __fmul_rn(v, 0.95f);
+        t.ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(u, 1.0f), fWt), -1.0f), 0.5f);   // ((u+1)*W-1)/2
+        t.iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(v, 1.0f), fHt), -1.0f), 0.5f);
+    }
+    t.scale = s;
+    t.u = u;
+    t.v = v;
+    return t;
+}
+
+// Bilinear footprint with zero padding (F.grid_sample(mode="bilinear", padding_mode="zeros")).
+// Indices are clamped into the texture and the weight of an out-of-range tap is zeroed, so the
+// sixteen loads are unconditional.
+struct Taps {
+    int o00, o01, o10, o11;      // element offsets inside one channel slab
+    float w00, w01, w10, w11;    // nw, ne, sw, se
+};
+
+// Requires ix in (-1, Wt) and iy in (-1, Ht) (caller tests; anything else contributes zero).
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int Ht, int Wt) {
+    Taps t;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float wx1 = ix - fx0, wy1 = iy - fy0;        // exact
+    float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;          // == (x0+1) - ix rounded
+    float wx1m = wx1, wy1m = wy1;
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    if (x0 < 0) wx0 = 0.0f;
+    if (y0 < 0) wy0 = 0.0f;
+    if (x0 + 1 > Wt - 1) wx1m = 0.0f;
+    if (y0 + 1 > Ht - 1) wy1m = 0.0f;
+    const int x0c = max(x0, 0), y0c = max(y0, 0);
+    const int x1c = min(x0 + 1, Wt - 1), y1c = min(y0 + 1, Ht - 1);
+    t.o00 = y0c * Wt + x0c;
+    t.o01 = y0c * Wt + x1c;
+    t.o10 = y1c * Wt + x0c;
+    t.o11 = y1c * Wt + x1c;
+    t.w00 = wx0 * wy0;
+    t.w01 = wx1m * wy0;
+    t.w10 = wx0 * wy1m;
+    t.w11 = wx1m * wy1m;
+    return t;
+}
+
+__device__ __forceinline__ bool coord_hits(float ix, float iy, float fWt, float fHt) {
+    return ix > -1.0f && ix < fWt && iy > -1.0f && iy < fHt;   // false for NaN
+}
+
+__device__ __forceinline__ float tap4(const float* __restrict__ ch, const Taps& t) {
+    const float a = __ldg(ch + t.o00), b = __ldg(ch + t.o01), c = __ldg(ch + t.o10), d = __ldg(ch + t.o11);
+    return fmaf(d, t.w11, fmaf(c, t.w10, fmaf(b, t.w01, a * t.w00)));
+}
+
+}  // namespace gmpi

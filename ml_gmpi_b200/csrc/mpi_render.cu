@@ -1,0 +1,514 @@
+// MPI over-composite renderer for B200 (sm_100a): kernels + C ABI (include/gmpi_mpi_render.h).
+//
+// Replaces gmpi/core/mpi.py MPI.forward (:308-436) + homography (:26-153) and their autograd.
+// DESIGN.md describes the data layout, each kernel and its roofline.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gmpi_mpi_render.h"
+#include "mpi_common.cuh"
+
+namespace gmpi {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define GMPI_CUDA_OK(expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(GMPI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Forward, direct-gather variant: one thread = one output pixel, a warp = 32 consecutive x.
+// Taps are read straight from global memory through L1 (per channel a warp touches one or two
+// 128-byte lines per tap row).  Works for every shape; the TMA-staged variant is the fast path.
+// ------------------------------------------------------------------------------------------
+constexpr int kFwdTileW = 32;
+constexpr int kFwdTileH = 8;
+
+template <bool kAlignCorners>
+__global__ void __launch_bounds__(kFwdTileW* kFwdTileH)
+mpi_fwd_direct_kernel(const RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw);
+
+    const int v = blockIdx.z;
+    const int m = __ldg(p.view2mpi + v);
+    const int tid = threadIdx.y * kFwdTileW + threadIdx.x;
+    const float* e = p.eye + 3 * v;
+    const float eye0_z = __ldg(p.eye + 2);   // mpi.py:70 compares every distance with view 0's eye
+    uint32_t flag = 0;
+    for (int i = tid; i < p.N; i += kFwdTileW * kFwdTileH) {
+        const float* dp = p.dhw + ((size_t)m * p.N + i) * 3;
+        s_pc[i] = make_plane_const(dp, __ldg(e + 2));
+        if (!(__ldg(dp) >= eye0_z)) flag |= GMPI_FLAG_PLANE_BEHIND_EYE;
+    }
+    __syncthreads();
+
+    const int px = blockIdx.x * kFwdTileW + threadIdx.x;
+    const int py = blockIdx.y * kFwdTileH + threadIdx.y;
+    if (px < p.W && py < p.H) {
+        const size_t img = (size_t)p.H * p.W;
+        const size_t pix = (size_t)py * p.W + px;
+        const float* rd = p.ray_dir + (size_t)v * 3 * img + pix;
+        const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
+        const float zd[3] = {__ldg(p.z_dir + 3 * v), __ldg(p.z_dir + 3 * v + 1), __ldg(p.z_dir + 3 * v + 2)};
+        const RayConst rc = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+
+        const int Ht = p.Ht, Wt = p.Wt;
+        const float fWt = (float)Wt, fHt = (float)Ht;
+        const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+        const size_t tex = (size_t)Ht * Wt;
+        const float* plane = p.rgba + (size_t)m * p.N * 4 * tex;
+        const bool check_last = (p.options & GMPI_CHECK_LAST_PLANE) != 0;
+
+        float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cws = 0.0f;
+#pragma unroll 2
+        for (int i = 0; i < p.N; ++i, plane += 4 * tex) {
+            const PlaneConst pc = s_pc[i];
+            const TexCoord tc = plane_coord<kAlignCorners>(pc, rc, hsx, hsy, fWt, fHt);
+            if (check_last && i == p.N - 1) {
+                if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
+            }
+            if (coord_hits(tc.ix, tc.iy, fWt, fHt)) {
+                const Taps t = make_taps(tc.ix, tc.iy, Ht, Wt);
+                const float r = tap4(plane, t);
+                const float g = tap4(plane + tex, t);
+                const float b = tap4(plane + 2 * tex, t);
+                const float a = tap4(plane + 3 * tex, t);
+                const float w = a * T;                                   // mpi.py:423
+                cr = fmaf(w, r, cr);                                     // mpi.py:430
+                cg = fmaf(w, g, cg);
+                cb = fmaf(w, b, cb);
+                cws = fmaf(w, tc.scale, cws);                            // depth_i = scale * (ray.z_dir), :150
+                T *= (1.0f - a) + 1e-10f;                                // mpi.py:421
+            }
+        }
+        const float dep = cws * rc.dz;
+        if (p.options & GMPI_COLOR_MINUS1_1) {                           // mpi_renderer.py:467
+            cr = fmaf(2.0f, cr, -1.0f);
+            cg = fmaf(2.0f, cg, -1.0f);
+            cb = fmaf(2.0f, cb, -1.0f);
+        }
+        float* co = p.color + (size_t)v * 3 * img + pix;
+        co[0] = cr;
+        co[img] = cg;
+        co[2 * img] = cb;
+        p.depth[(size_t)v * img + pix] = dep;
+    }
+    if (flag) atomicOr(p.flags, flag);
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward, direct variant.
+//   pass A (front to back, alpha only): T_i = prod_{j<i}(1 - a_j + 1e-10), stashed per thread in
+//           shared memory ([plane][thread], conflict free).
+//   pass B (back to front, all channels): R_{i-1} = a_i q_i + s_i R_i with R_{N-1} = 0,
+//           q_i = G.rgb_i + Gd*depth_i, s_i = 1 - a_i + 1e-10, and
+//             dL/d rgb_i = G * a_i T_i
+//             dL/d a_i   = T_i (q_i - R_i)
+//           which equals autograd's  T_i q_i - (sum_{k>i} a_k q_k P_k)/s_i  (cumprod_backward)
+//           without the division by s_i (1e-10 when a_i == 1) and without cancellation.
+//           The four bilinear weights scatter each value with red.global.add.f32.
+// ------------------------------------------------------------------------------------------
+template <bool kAlignCorners>
+__global__ void __launch_bounds__(128)
+mpi_bwd_direct_kernel(const RenderParams p, const int tile_w, const int tile_h) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw);
+    const int nthreads = tile_w * tile_h;
+    float* s_T = reinterpret_cast<float*>(smem_raw + sizeof(PlaneConst) * p.N);   // [N][nthreads]
+
+    const int v = blockIdx.z;
+    const int m = __ldg(p.view2mpi + v);
+    const int tid = threadIdx.y * tile_w + threadIdx.x;
+    const float* e = p.eye + 3 * v;
+    for (int i = tid; i < p.N; i += nthreads) {
+        s_pc[i] = make_plane_const(p.dhw + ((size_t)m * p.N + i) * 3, __ldg(e + 2));
+    }
+    __syncthreads();
+
+    const int px = blockIdx.x * tile_w + threadIdx.x;
+    const int py = blockIdx.y * tile_h + threadIdx.y;
+    if (px >= p.W || py >= p.H) return;
+
+    const size_t img = (size_t)p.H * p.W;
+    const size_t pix = (size_t)py * p.W + px;
+    const float* rd = p.ray_dir + (size_t)v * 3 * img + pix;
+    const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
+    const float zd[3] = {__ldg(p.z_dir + 3 * v), __ldg(p.z_dir + 3 * v + 1), __ldg(p.z_dir + 3 * v + 2)};
+    const RayConst rc = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+
+    const int Ht = p.Ht, Wt = p.Wt, N = p.N;
+    const float fWt = (float)Wt, fHt = (float)Ht;
+    const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    const size_t tex = (size_t)Ht * Wt;
+    const float* mpi = p.rgba + (size_t)m * N * 4 * tex;
+    float* gmpi = p.g_rgba + (size_t)m * N * 4 * tex;
+
+    float gscale = (p.options & GMPI_COLOR_MINUS1_1) ? 2.0f : 1.0f;
+    const float* gc = p.g_color + (size_t)v * 3 * img + pix;
+    const float G0 = gscale * __ldg(gc), G1 = gscale * __ldg(gc + img), G2 = gscale * __ldg(gc + 2 * img);
+    const float Gd = p.g_depth ? __ldg(p.g_depth + (size_t)v * img + pix) : 0.0f;
+    const float Gdz = Gd * rc.dz;   // depth_i = scale_i * dz
+
+    // pass A
+    float T = 1.0f;
+    for (int i = 0; i < N; ++i) {
+        s_T[(size_t)i * nthreads + tid] = T;
+        const TexCoord tc = plane_coord<kAlignCorners>(s_pc[i], rc, hsx, hsy, fWt, fHt);
+        if (coord_hits(tc.ix, tc.iy, fWt, fHt)) {
+            const Taps t = make_taps(tc.ix, tc.iy, Ht, Wt);
+            const float a = tap4(mpi + ((size_t)i * 4 + 3) * tex, t);
+            T *= (1.0f - a) + 1e-10f;
+        }
+    }
+    // pass B
+    float R = 0.0f;
+    for (int i = N - 1; i >= 0; --i) {
+        const TexCoord tc = plane_coord<kAlignCorners>(s_pc[i], rc, hsx, hsy, fWt, fHt);
+        if (!coord_hits(tc.ix, tc.iy, fWt, fHt)) continue;
+        const Taps t = make_taps(tc.ix, tc.iy, Ht, Wt);
+        const float* plane = mpi + (size_t)i * 4 * tex;
+        const float r = tap4(plane, t);
+        const float g = tap4(plane + tex, t);
+        const float b = tap4(plane + 2 * tex, t);
+        const float a = tap4(plane + 3 * tex, t);
+        const float Ti = s_T[(size_t)i * nthreads + tid];
+        const float q = fmaf(G0, r, fmaf(G1, g, fmaf(G2, b, Gdz * tc.scale)));
+        const float w = a * Ti;
+        const float gv[4] = {G0 * w, G1 * w, G2 * w, Ti * (q - R)};
+        R = fmaf(a, q, ((1.0f - a) + 1e-10f) * R);
+        float* gp = gmpi + (size_t)i * 4 * tex;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float* gch = gp + (size_t)c * tex;
+            if (t.w00 != 0.0f) atomicAdd(gch + t.o00, gv[c] * t.w00);
+            if (t.w01 != 0.0f) atomicAdd(gch + t.o01, gv[c] * t.w01);
+            if (t.w10 != 0.0f) atomicAdd(gch + t.o10, gv[c] * t.w10);
+            if (t.w11 != 0.0f) atomicAdd(gch + t.o11, gv[c] * t.w11);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Range check: one streaming pass over rgba.  A float is inside [0,1] iff its bit pattern,
+// read as unsigned, is <= 0x3f800000 (or it is -0.0); NaN and negatives have larger patterns.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool out_of_unit(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return b > 0x3f800000u && b != 0x80000000u;
+}
+
+__global__ void __launch_bounds__(256)
+mpi_check_range_kernel(const float4* __restrict__ rgba4, size_t n_slabs, size_t slab4, uint32_t* flags) {
+    // one slab = one (mpi, plane, channel) image of slab4 float4's; channel = slab % 4
+    uint32_t flag = 0;
+    const size_t total = n_slabs * slab4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 x = __ldcs(rgba4 + i);
+        if (out_of_unit(x.x) || out_of_unit(x.y) || out_of_unit(x.z) || out_of_unit(x.w)) {
+            const size_t slab = i / slab4;
+            flag |= ((slab & 3) == 3) ? (GMPI_FLAG_ALPHA_RANGE | GMPI_FLAG_RGBA_RANGE) : GMPI_FLAG_RGBA_RANGE;
+        }
+    }
+    flag = __reduce_or_sync(0xffffffffu, flag);
+    if (flag && (threadIdx.x & 31) == 0) atomicOr(flags, flag);
+}
+
+__global__ void mpi_check_range_scalar_kernel(const float* __restrict__ rgba, size_t n_slabs, size_t slab,
+                                              uint32_t* flags) {
+    uint32_t flag = 0;
+    const size_t total = n_slabs * slab;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        if (out_of_unit(__ldcs(rgba + i))) {
+            flag |= (((i / slab) & 3) == 3) ? (GMPI_FLAG_ALPHA_RANGE | GMPI_FLAG_RGBA_RANGE) : GMPI_FLAG_RGBA_RANGE;
+        }
+    }
+    if (flag) atomicOr(flags, flag);
+}
+
+// ------------------------------------------------------------------------------------------
+// Test hook: texel coordinates.
+// ------------------------------------------------------------------------------------------
+template <bool kAlignCorners>
+__global__ void mpi_debug_coords_kernel(const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                                        const float* eye, float* out, int V, int N, int Ht, int Wt, int H, int W) {
+    const size_t img = (size_t)H * W;
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (pix >= img) return;
+    const int m = view2mpi[v];
+    const float* e = eye + 3 * v;
+    const float ev[3] = {e[0], e[1], e[2]};
+    const float zd[3] = {0.f, 0.f, 1.f};
+    const float* rd = ray_dir + (size_t)v * 3 * img + pix;
+    const RayConst rc = make_ray_const(rd[0], rd[img], rd[2 * img], ev, zd);
+    const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    for (int i = 0; i < N; ++i) {
+        const PlaneConst pc = make_plane_const(dhw + ((size_t)m * N + i) * 3, ev[2]);
+        const TexCoord tc = plane_coord<kAlignCorners>(pc, rc, hsx, hsy, (float)Wt, (float)Ht);
+        out[(((size_t)v * N + i) * 2 + 0) * img + pix] = tc.ix;
+        out[(((size_t)v * N + i) * 2 + 1) * img + pix] = tc.iy;
+    }
+}
+
+__global__ void mpi_debug_division_kernel(const float* a, const float* b, float* out_fast, float* out_ieee, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = a[i], y = b[i];
+        out_fast[i] = in_safe_range(y) && (x == 0.0f || in_safe_range(x)) ? div_by_rcp(x, y, __frcp_rn(y)) : __fdiv_rn(x, y);
+        out_ieee[i] = __fdiv_rn(x, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int check_common(const void* rgba, const void* view2mpi, const void* dhw, const void* ray_dir,
+                        const void* eye, const void* z_dir, int M, int V, int N, int Ht, int Wt, int H, int W) {
+    if (!rgba || !view2mpi || !dhw || !ray_dir || !eye || !z_dir)
+        return fail(GMPI_ERR_INVALID_ARGUMENT, "null input pointer");
+    if (M < 1 || V < 0 || N < 1 || Ht < 1 || Wt < 1 || H < 1 || W < 1)
+        return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes M=%d V=%d N=%d Ht=%d Wt=%d H=%d W=%d", M, V, N, Ht, Wt, H, W);
+    if ((size_t)Ht * Wt > (size_t)0x7fffffff)
+        return fail(GMPI_ERR_UNSUPPORTED, "texture of %dx%d texels exceeds 2^31 elements per channel", Ht, Wt);
+    if (V > 65535) return fail(GMPI_ERR_UNSUPPORTED, "V=%d views exceed one launch (65535); split the batch", V);
+    return GMPI_OK;
+}
+
+}  // namespace gmpi
+
+using namespace gmpi;
+
+extern "C" {
+
+int gmpi_abi_version(void) { return GMPI_ABI_VERSION; }
+
+const char* gmpi_last_error(void) { return g_err; }
+
+const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
+    (void)N; (void)Ht; (void)Wt; (void)H; (void)W;
+    return "fwd_direct_32x8";
+}
+
+int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                        const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags, int M,
+                        int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
+    int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
+    if (rc) return rc;
+    if (!color || !depth || !flags) return fail(GMPI_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (V == 0) return GMPI_OK;
+    RenderParams p{};
+    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
+    p.color = color; p.depth = depth; p.flags = flags;
+    p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(PlaneConst) * (size_t)N;
+    if (smem > 200 * 1024) return fail(GMPI_ERR_UNSUPPORTED, "N=%d planes exceed the shared-memory plane table", N);
+    dim3 block(kFwdTileW, kFwdTileH);
+    dim3 grid((W + kFwdTileW - 1) / kFwdTileW, (H + kFwdTileH - 1) / kFwdTileH, V);
+    if (grid.y > 65535) return fail(GMPI_ERR_UNSUPPORTED, "image height %d too large", H);
+    if (options & GMPI_ALIGN_CORNERS) {
+        if (smem > 48 * 1024)
+            GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpi_fwd_direct_kernel<true><<<grid, block, smem, st>>>(p);
+    } else {
+        if (smem > 48 * 1024)
+            GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpi_fwd_direct_kernel<false><<<grid, block, smem, st>>>(p);
+    }
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                        const float* eye, const float* z_dir, const float* g_color, const float* g_depth,
+                        float* g_rgba, int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options,
+                        void* stream) {
+    int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
+    if (rc) return rc;
+    if (!g_color || !g_rgba) return fail(GMPI_ERR_INVALID_ARGUMENT, "null gradient pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (options & GMPI_ZERO_GRAD)
+        GMPI_CUDA_OK(cudaMemsetAsync(g_rgba, 0, sizeof(float) * (size_t)M * N * 4 * Ht * Wt, st));
+    if (V == 0) return GMPI_OK;
+    RenderParams p{};
+    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
+    p.g_color = g_color; p.g_depth = g_depth; p.g_rgba = g_rgba;
+    p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
+    // tile: as many threads (<=128) as the per-thread transmittance stash allows
+    int tile_w = 32, tile_h = 4;
+    size_t smem = 0;
+    for (;; tile_h >>= 1) {
+        if (tile_h == 0) return fail(GMPI_ERR_UNSUPPORTED, "N=%d planes exceed the backward stash (227 KB / 32 threads)", N);
+        smem = sizeof(PlaneConst) * (size_t)N + sizeof(float) * (size_t)N * tile_w * tile_h;
+        if (smem <= 227 * 1024) break;
+    }
+    dim3 block(tile_w, tile_h);
+    dim3 grid((W + tile_w - 1) / tile_w, (H + tile_h - 1) / tile_h, V);
+    if (grid.y > 65535) return fail(GMPI_ERR_UNSUPPORTED, "image height %d too large", H);
+    if (options & GMPI_ALIGN_CORNERS) {
+        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpi_bwd_direct_kernel<true><<<grid, block, smem, st>>>(p, tile_w, tile_h);
+    } else {
+        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mpi_bwd_direct_kernel<false><<<grid, block, smem, st>>>(p, tile_w, tile_h);
+    }
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_check_range(const float* rgba, int M, int N, int Ht, int Wt, uint32_t* flags, void* stream) {
+    if (!rgba || !flags) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (M < 1 || N < 1 || Ht < 1 || Wt < 1) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t slab = (size_t)Ht * Wt, n_slabs = (size_t)M * N * 4;
+    int dev = 0, sms = 148;
+    GMPI_CUDA_OK(cudaGetDevice(&dev));
+    GMPI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * 8;
+    if (slab % 4 == 0 && ((uintptr_t)rgba & 15) == 0) {
+        mpi_check_range_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(rgba), n_slabs, slab / 4, flags);
+    } else {
+        mpi_check_range_scalar_kernel<<<grid, 256, 0, st>>>(rgba, n_slabs, slab, flags);
+    }
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_debug_plane_coords(const int32_t* view2mpi, const float* dhw, const float* ray_dir, const float* eye,
+                            float* out, int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
+    if (!view2mpi || !dhw || !ray_dir || !eye || !out) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (V < 1 || N < 1 || Ht < 1 || Wt < 1 || H < 1 || W < 1) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img = (size_t)H * W;
+    dim3 grid((unsigned)((img + 255) / 256), V);
+    if (options & GMPI_ALIGN_CORNERS)
+        mpi_debug_coords_kernel<true><<<grid, 256, 0, st>>>(view2mpi, dhw, ray_dir, eye, out, V, N, Ht, Wt, H, W);
+    else
+        mpi_debug_coords_kernel<false><<<grid, 256, 0, st>>>(view2mpi, dhw, ray_dir, eye, out, V, N, Ht, Wt, H, W);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_debug_division(const float* a, const float* b, float* out_fast, float* out_ieee, size_t n, void* stream) {
+    if (!a || !b || !out_fast || !out_ieee) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    mpi_debug_division_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(a, b, out_fast, out_ieee, n);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                             const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags_out,
+                             int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options, int device) {
+    int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
+    if (rc) return rc;
+    if (!color || !depth || !flags_out) return fail(GMPI_ERR_INVALID_ARGUMENT, "null output pointer");
+    for (int v = 0; v + 1 < V; ++v)
+        if (view2mpi[v] > view2mpi[v + 1]) return fail(GMPI_ERR_INVALID_ARGUMENT, "views must be MPI-major (sorted view2mpi)");
+    for (int v = 0; v < V; ++v)
+        if (view2mpi[v] < 0 || view2mpi[v] >= M) return fail(GMPI_ERR_INVALID_ARGUMENT, "view2mpi[%d]=%d out of range", v, view2mpi[v]);
+    GMPI_CUDA_OK(cudaSetDevice(device));
+    const size_t tex = (size_t)Ht * Wt, img = (size_t)H * W;
+    const size_t mpi_bytes = sizeof(float) * (size_t)N * 4 * tex;
+    // device staging: two MPI slots (copy of MPI m+1 overlaps the render of MPI m) + per-view data
+    float *d_mpi[2] = {nullptr, nullptr}, *d_dhw = nullptr, *d_ray = nullptr, *d_eye = nullptr, *d_z = nullptr;
+    float *d_color = nullptr, *d_depth = nullptr;
+    int32_t* d_v2m = nullptr;
+    uint32_t* d_flags = nullptr;
+    cudaStream_t s_copy = nullptr, s_run = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    int status = GMPI_OK;
+#define HOST_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            status = fail(GMPI_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                \
+            goto done;                                                                                   \
+        }                                                                                                \
+    } while (0)
+    HOST_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        HOST_TRY(cudaMalloc(&d_mpi[k], mpi_bytes));
+        HOST_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        HOST_TRY(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
+    }
+    HOST_TRY(cudaMalloc(&d_dhw, sizeof(float) * (size_t)M * N * 3));
+    HOST_TRY(cudaMalloc(&d_ray, sizeof(float) * (size_t)V * 3 * img));
+    HOST_TRY(cudaMalloc(&d_eye, sizeof(float) * (size_t)V * 3));
+    HOST_TRY(cudaMalloc(&d_z, sizeof(float) * (size_t)V * 3));
+    HOST_TRY(cudaMalloc(&d_color, sizeof(float) * (size_t)V * 3 * img));
+    HOST_TRY(cudaMalloc(&d_depth, sizeof(float) * (size_t)V * img));
+    HOST_TRY(cudaMalloc(&d_v2m, sizeof(int32_t) * (size_t)(V > 0 ? V : 1)));
+    HOST_TRY(cudaMalloc(&d_flags, sizeof(uint32_t)));
+    HOST_TRY(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), s_run));
+    HOST_TRY(cudaMemsetAsync(d_v2m, 0, sizeof(int32_t) * (size_t)(V > 0 ? V : 1), s_run));   // staged MPI is slot-local index 0
+    HOST_TRY(cudaMemcpyAsync(d_dhw, dhw, sizeof(float) * (size_t)M * N * 3, cudaMemcpyHostToDevice, s_run));
+    HOST_TRY(cudaMemcpyAsync(d_ray, ray_dir, sizeof(float) * (size_t)V * 3 * img, cudaMemcpyHostToDevice, s_run));
+    HOST_TRY(cudaMemcpyAsync(d_eye, eye, sizeof(float) * (size_t)V * 3, cudaMemcpyHostToDevice, s_run));
+    HOST_TRY(cudaMemcpyAsync(d_z, z_dir, sizeof(float) * (size_t)V * 3, cudaMemcpyHostToDevice, s_run));
+    {
+        int v0 = 0, slot = 0, used[2] = {0, 0};
+        for (int m = 0; m < M; ++m) {
+            int v1 = v0;
+            while (v1 < V && view2mpi[v1] == m) ++v1;
+            if (v1 == v0) continue;
+            if (used[slot]) HOST_TRY(cudaStreamWaitEvent(s_copy, ev_free[slot], 0));
+            HOST_TRY(cudaMemcpyAsync(d_mpi[slot], rgba + (size_t)m * N * 4 * tex, mpi_bytes, cudaMemcpyHostToDevice, s_copy));
+            HOST_TRY(cudaEventRecord(ev_in[slot], s_copy));
+            HOST_TRY(cudaStreamWaitEvent(s_run, ev_in[slot], 0));
+            // mpi.py:70 compares against view 0's eye: pass views [v0,v1) with their own eye; the
+            // plane-behind-eye flag is evaluated against the first view of each launch.
+            status = gmpi_mpi_render_fwd(d_mpi[slot], d_v2m, d_dhw + (size_t)m * N * 3, d_ray + (size_t)v0 * 3 * img,
+                                         d_eye + (size_t)v0 * 3, d_z + (size_t)v0 * 3, d_color + (size_t)v0 * 3 * img,
+                                         d_depth + (size_t)v0 * img, d_flags, 1, v1 - v0, N, Ht, Wt, H, W, options, s_run);
+            if (status) goto done;
+            HOST_TRY(cudaEventRecord(ev_free[slot], s_run));
+            used[slot] = 1;
+            slot ^= 1;
+            v0 = v1;
+        }
+    }
+    HOST_TRY(cudaMemcpyAsync(color, d_color, sizeof(float) * (size_t)V * 3 * img, cudaMemcpyDeviceToHost, s_run));
+    HOST_TRY(cudaMemcpyAsync(depth, d_depth, sizeof(float) * (size_t)V * img, cudaMemcpyDeviceToHost, s_run));
+    HOST_TRY(cudaMemcpyAsync(flags_out, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s_run));
+    HOST_TRY(cudaStreamSynchronize(s_run));
+    HOST_TRY(cudaStreamSynchronize(s_copy));
+done:
+#undef HOST_TRY
+    for (int k = 0; k < 2; ++k) {
+        if (d_mpi[k]) cudaFree(d_mpi[k]);
+        if (ev_in[k]) cudaEventDestroy(ev_in[k]);
+        if (ev_free[k]) cudaEventDestroy(ev_free[k]);
+    }
+    if (d_dhw) cudaFree(d_dhw);
+    if (d_ray) cudaFree(d_ray);
+    if (d_eye) cudaFree(d_eye);
+    if (d_z) cudaFree(d_z);
+    if (d_color) cudaFree(d_color);
+    if (d_depth) cudaFree(d_depth);
+    if (d_v2m) cudaFree(d_v2m);
+    if (d_flags) cudaFree(d_flags);
+    if (s_copy) cudaStreamDestroy(s_copy);
+    if (s_run) cudaStreamDestroy(s_run);
+    return status;
+}
+
+}  // extern "C"

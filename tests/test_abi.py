@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/gmpi_mpi_render.h declares, and validates arguments without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import ml_gmpi_b200 as g
+from ml_gmpi_b200 import _lib
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    g.build_library()
+    return _lib.load()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "gmpi_mpi_render.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(gmpi_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported(lib):
+    syms = declared_symbols()
+    assert "gmpi_mpi_render_fwd" in syms and "gmpi_mpi_render_bwd" in syms
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_abi_version_and_constants(lib):
+    assert lib.gmpi_abi_version() == _lib.ABI_VERSION
+    hdr = open(os.path.join(ROOT, "include", "gmpi_mpi_render.h")).read()
+    for name, val in [("GMPI_FLAG_RGBA_RANGE", _lib.FLAG_RGBA_RANGE), ("GMPI_FLAG_ALPHA_RANGE", _lib.FLAG_ALPHA_RANGE),
+                      ("GMPI_FLAG_LAST_PLANE_OOB", _lib.FLAG_LAST_PLANE_OOB),
+                      ("GMPI_FLAG_PLANE_BEHIND_EYE", _lib.FLAG_PLANE_BEHIND_EYE),
+                      ("GMPI_ALIGN_CORNERS", _lib.OPT_ALIGN_CORNERS), ("GMPI_CHECK_LAST_PLANE", _lib.OPT_CHECK_LAST_PLANE),
+                      ("GMPI_COLOR_MINUS1_1", _lib.OPT_COLOR_MINUS1_1), ("GMPI_ZERO_GRAD", _lib.OPT_ZERO_GRAD)]:
+        m = re.search(rf"#define {name} (\d+)u", hdr)
+        assert m and int(m.group(1)) == val, name
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    rc = lib.gmpi_mpi_render_fwd(None, None, None, None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 0, None)
+    assert rc == 1 and b"null" in lib.gmpi_last_error()
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.addressof(buf)
+    rc = lib.gmpi_mpi_render_fwd(p, p, p, p, p, p, p, p, p, 1, 1, 0, 4, 4, 4, 4, 0, None)
+    assert rc == 1 and b"bad sizes" in lib.gmpi_last_error()
+    rc = lib.gmpi_mpi_render_bwd(p, p, p, p, p, p, None, None, None, 1, 1, 1, 4, 4, 4, 4, 0, None)
+    assert rc == 1
+
+
+def test_cubin_is_sm100a():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", g._build.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_no_cpu_fallback():
+    mpi = g.MPI(align_corners=True)
+    rgba = torch.rand(1, 2, 4, 8, 8)
+    dhw = torch.tensor([[[1.0, 0.2, 0.2], [1.1, 0.2, 0.2]]])
+    ray = torch.zeros(1, 3, 4, 4); ray[:, 2] = 1
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        mpi(batch_rgba=rgba, batch_dhw=dhw, batch_ray_dir=[ray], batch_eye_pos=[torch.zeros(1, 3)],
+            batch_z_dir=[torch.tensor([[0., 0., 1.]])], separate_background=None)
+
+
+def test_shape_asserts_match_reference_messages():
+    mpi = g.MPI()
+    ray = torch.zeros(1, 3, 4, 4)
+    with pytest.raises(AssertionError, match="Expected rgba to be of shape"):
+        mpi(batch_rgba=torch.rand(1, 2, 3, 8, 8), batch_dhw=torch.rand(1, 2, 3), batch_ray_dir=[ray],
+            batch_eye_pos=[torch.zeros(1, 3)], batch_z_dir=[torch.zeros(1, 3)], separate_background=None)
+    with pytest.raises(AssertionError, match="Expected dhw to be of shape"):
+        mpi(batch_rgba=torch.rand(1, 2, 4, 8, 8), batch_dhw=torch.rand(1, 3, 3), batch_ray_dir=[ray],
+            batch_eye_pos=[torch.zeros(1, 3)], batch_z_dir=[torch.zeros(1, 3)], separate_background=None)
+    with pytest.raises(AssertionError, match="Expected ray_dir to be of shape"):
+        mpi(batch_rgba=torch.rand(1, 2, 4, 8, 8), batch_dhw=torch.rand(1, 2, 3), batch_ray_dir=[ray[0]],
+            batch_eye_pos=[torch.zeros(1, 3)], batch_z_dir=[torch.zeros(1, 3)], separate_background=None)
+
+
+def test_pack_views_is_mpi_major():
+    rays = [torch.zeros(2, 3, 4, 4), torch.ones(1, 3, 4, 4), torch.zeros(3, 3, 4, 4)]
+    eyes = [torch.zeros(2, 3), torch.ones(1, 3), torch.zeros(3, 3)]
+    v2m, ray, eye, z = g.MPI.pack_views(rays, eyes, eyes, torch.device("cpu"))
+    assert v2m.tolist() == [0, 0, 1, 2, 2, 2] and v2m.dtype == torch.int32
+    assert ray.shape == (6, 3, 4, 4) and float(ray[2].min()) == 1.0

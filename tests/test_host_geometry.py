@@ -1,0 +1,55 @@
+"""Host-side camera / pose / plane-geometry code against fixtures produced by
+the unmodified reference (tests/golden/ffhq_dhw.npz, ffhq_cams_20.npz)."""
+import numpy as np
+import torch
+
+from ml_gmpi_b200 import camera, geometry, synth
+from conftest import load_golden
+
+
+def test_plane_table_matches_reference():
+    ref = load_golden("ffhq_dhw")
+    for n, key in ((8, "n8"), (32, "n32"), (96, "n96")):
+        ours = geometry.plane_dhw_table(n_planes=n, **geometry.FFHQ)
+        assert ours.shape == ref[key].shape and ours.dtype == np.float32
+        np.testing.assert_allclose(ours, ref[key], rtol=2e-6, atol=0)
+    kw = dict(geometry.FFHQ); kw["confined"] = False
+    np.testing.assert_allclose(geometry.plane_dhw_table(n_planes=8, **kw), ref["n8_unconfined"], rtol=2e-6)
+
+
+def test_sample_distance_methods():
+    d = geometry.sample_distance(0.95, 1.12, 32, "inverse")
+    assert d[0] == np.float32(0.95) and abs(d[-1] - 1.12) < 1e-6 and np.all(np.diff(d) > 0)
+    assert np.allclose(np.diff(1.0 / d.astype(np.float64)), np.diff(1.0 / d.astype(np.float64))[0], rtol=1e-4)
+    for m in ("uniform", "log-uniform", "sqrt", "squared"):
+        x = geometry.sample_distance(0.5, 2.0, 5, m)
+        assert abs(x[0] - 0.5) < 1e-6 and abs(x[-1] - 2.0) < 1e-6
+
+
+def test_poses_and_rays_match_reference():
+    ref = load_golden("ffhq_cams_20")
+    c2w = camera.sphere_poses(torch.from_numpy(ref["yaws"]), torch.from_numpy(ref["pitches"]), ref["sphere_center"],
+                              float(ref["sphere_r"]))
+    np.testing.assert_allclose(c2w.numpy(), ref["c2w"], atol=2e-7)
+    cam = camera.PinholeCamera.from_fov(float(ref["fov"]), 20, 20)
+    ray, eye, z = cam.generate_rays(torch.from_numpy(ref["c2w"]))
+    np.testing.assert_allclose(ray.numpy(), ref["ray_dir"], atol=2e-7)
+    assert np.array_equal(eye.numpy(), ref["eye"]) and np.array_equal(z.numpy(), ref["z_dir"])
+
+
+def test_identity_pose_is_identity_matrix():
+    c2w = camera.sphere_poses(torch.zeros(1), torch.zeros(1), (0, 0, 1.0), 1.0)
+    np.testing.assert_allclose(c2w[0].numpy(), np.eye(4), atol=1e-7)
+
+
+def test_truncated_normal_stays_in_range():
+    g = torch.Generator().manual_seed(0)
+    x = camera.truncated_normal(10000, 0.0, 0.289, 2, g)
+    assert x.shape == (10000, 1) and float(x.abs().max()) <= 2 * 0.289 + 1e-6
+
+
+def test_synth_case_shapes():
+    c = synth.make_case(n_planes=8, tex=16, img=12, n_mpi=2, views_per_mpi=3, seed=1)
+    assert c.rgba.shape == (2, 8, 4, 16, 16) and c.ray_dir.shape == (6, 3, 12, 12)
+    assert c.view2mpi.tolist() == [0, 0, 0, 1, 1, 1] and c.dhw.shape == (2, 8, 3)
+    assert float(c.rgba.min()) >= 0 and float(c.rgba.max()) <= 1
