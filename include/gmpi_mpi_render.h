@@ -114,6 +114,9 @@ int gmpi_debug_plane_coords(const int32_t* view2mpi, const float* dhw, const flo
                             const float* eye, float* out, int V, int N, int Ht, int Wt, int H,
                             int W, uint32_t options, void* stream);
 
+/* Test hook: force the forward kernel variant: 0 auto (default), 1 direct-gather, 2 TMA-staged. */
+int gmpi_debug_set_fwd_variant(int variant);
+
 /* Test hook: out_fast[i] = the kernels' reciprocal+FMA division a[i]/b[i]; out_ieee[i] = div.rn.f32. */
 int gmpi_debug_division(const float* a, const float* b, float* out_fast, float* out_ieee, size_t n,
                         void* stream);

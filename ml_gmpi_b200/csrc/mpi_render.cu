@@ -10,6 +10,7 @@
 
 #include "../../include/gmpi_mpi_render.h"
 #include "mpi_common.cuh"
+#include "mpi_fwd_staged.cuh"
 
 namespace gmpi {
 
@@ -302,9 +303,27 @@ int gmpi_abi_version(void) { return GMPI_ABI_VERSION; }
 
 const char* gmpi_last_error(void) { return g_err; }
 
+static int g_fwd_variant = 0;   // 0 auto, 1 direct, 2 staged
+
+int gmpi_debug_set_fwd_variant(int variant) {
+    if (variant < 0 || variant > 2) return fail(GMPI_ERR_INVALID_ARGUMENT, "variant must be 0 (auto), 1 (direct) or 2 (staged)");
+    g_fwd_variant = variant;
+    return GMPI_OK;
+}
+
+// staged needs 16-byte row strides for the tensor map and enough tiles to fill the persistent grid
+static bool staged_eligible(int V, int Ht, int Wt, int H, int W) {
+    (void)Ht;
+    if (Wt % 4 != 0) return false;
+    if (g_fwd_variant == 2) return true;
+    if (g_fwd_variant == 1) return false;
+    const long tiles = (long)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * V;
+    return tiles >= 120;
+}
+
 const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
-    (void)N; (void)Ht; (void)Wt; (void)H; (void)W;
-    return "fwd_direct_32x8";
+    (void)N;
+    return staged_eligible(1 << 20, Ht, Wt, H, W) ? "fwd_staged_tma_64x32" : "fwd_direct_32x8";
 }
 
 int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
@@ -319,6 +338,31 @@ int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float*
     p.color = color; p.depth = depth; p.flags = flags;
     p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
     cudaStream_t st = (cudaStream_t)stream;
+    if (staged_eligible(V, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)) {
+        TmaMaps maps;
+        bool ok = true;
+        for (int k = 0; k < kNumMaps && ok; ++k)
+            ok = encode_plane_map(&maps.m[k], rgba, (uint64_t)M * N, Ht, Wt, kMinBW + k * kBWStep, kRowsPerOp) == 0;
+        if (!ok) {
+            if (g_fwd_variant == 2) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        } else {
+            int dev = 0, sms = 0;
+            GMPI_CUDA_OK(cudaGetDevice(&dev));
+            GMPI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+            const long n_tiles = (long)tiles_x * tiles_y * V;
+            const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+            if (options & GMPI_ALIGN_CORNERS) {
+                GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+                mpi_fwd_staged_kernel<true><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+            } else {
+                GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+                mpi_fwd_staged_kernel<false><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+            }
+            GMPI_CUDA_OK(cudaGetLastError());
+            return GMPI_OK;
+        }
+    }
     const size_t smem = sizeof(PlaneConst) * (size_t)N;
     if (smem > 200 * 1024) return fail(GMPI_ERR_UNSUPPORTED, "N=%d planes exceed the shared-memory plane table", N);
     dim3 block(kFwdTileW, kFwdTileH);

@@ -22,6 +22,15 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["direct", "staged"])
+def fwd_variant(request):
+    """Runs a forward test once per kernel variant (1 = direct gather, 2 = TMA-staged), then restores auto."""
+    lib = _lib.load()
+    _lib.check(lib.gmpi_debug_set_fwd_variant({"direct": 1, "staged": 2}[request.param]))
+    yield request.param
+    _lib.check(lib.gmpi_debug_set_fwd_variant(0))
+
+
 def groups(gd, device):
     v2m = gd["view2mpi"]
     M = gd["rgba"].shape[0]
@@ -31,7 +40,7 @@ def groups(gd, device):
 
 
 @pytest.mark.parametrize("name", MPI_CASES + ["c1_full_256"])
-def test_forward_matches_reference_golden(name):
+def test_forward_matches_reference_golden(name, fwd_variant):
     gd = load_golden(name)
     d = dev()
     rays, eyes, zs = groups(gd, d)
@@ -115,7 +124,7 @@ def test_fast_division_equals_ieee_division():
         assert np.array_equal(ieee.cpu().numpy().view(np.uint32), (a / b).view(np.uint32))
 
 
-def test_validate_full_raises_like_reference():
+def test_validate_full_raises_like_reference(fwd_variant):
     gd = load_golden("tiny_2mpi_3view")
     d = dev()
     rays, eyes, zs = groups(gd, d)
@@ -140,7 +149,7 @@ def test_validate_full_raises_like_reference():
             batch_z_dir=kw["batch_z_dir"], separate_background=None)
 
 
-def test_color_minus1_1_is_fused_affine():
+def test_color_minus1_1_is_fused_affine(fwd_variant):
     gd = load_golden("c1_small_64")
     d = dev()
     t = lambda a: torch.from_numpy(a).to(d)
@@ -178,7 +187,7 @@ def _ffhq_case(N, res, V, seed=1234, device=None):
 
 
 @pytest.mark.parametrize("N,res,V", [(32, 256, 8), (96, 512, 2), (96, 1024, 1)])
-def test_full_size_against_oracle(N, res, V):
+def test_full_size_against_oracle(N, res, V, fwd_variant):
     d = dev()
     case = _ffhq_case(N, res, V, device=d)
     color, depth = g.render_views(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir,
@@ -191,10 +200,12 @@ def test_full_size_against_oracle(N, res, V):
     assert rel_err(depth[v:v + 1].cpu().numpy(), rd) <= EXPECT
 
 
-def test_sanity_mode_all_alpha_one_shows_first_plane():
+def test_sanity_mode_all_alpha_one_shows_first_plane(fwd_variant):
     """eval/prepare_fake_data.py:51-56: alpha==1 everywhere => the render is the warped plane 0."""
     d = dev()
-    case = _ffhq_case(96, 512, 1, device=d)
+    from ml_gmpi_b200 import synth
+    # identity pose: every ray hits plane 0 (|u|,|v| <= 0.85 there); at oblique poses border rays miss it
+    case = synth.make_case(n_planes=96, tex=512, img=512, n_mpi=1, seed=1234, device=d, yaws=[0.0], pitches=[0.0])
     rgba = case.rgba.clone()
     rgba[:, :, 3] = 1.0
     color, depth = g.render_views(rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir)
@@ -204,7 +215,7 @@ def test_sanity_mode_all_alpha_one_shows_first_plane():
     assert rel_err(depth.cpu().numpy(), dfirst.cpu().numpy()) <= 1e-6
 
 
-def test_zero_alpha_renders_nothing_and_linearity_in_rgb():
+def test_zero_alpha_renders_nothing_and_linearity_in_rgb(fwd_variant):
     d = dev()
     case = _ffhq_case(32, 256, 2, device=d)
     rgba = case.rgba.clone()
@@ -236,3 +247,35 @@ def test_full_size_backward_c3_view_vs_oracle():
                               case.ray_dir.cpu().numpy(), case.eye.cpu().numpy(), case.z_dir.cpu().numpy(),
                               gc.cpu().numpy(), gdp.cpu().numpy())
     assert rel_err(rgba.grad.cpu().numpy(), ref) <= 2e-5
+
+
+def test_staged_falls_back_per_thread_for_non_projective_rays(fwd_variant):
+    """The staged kernel estimates a tile's texel footprint from its corner rays.  With rays that are NOT a pinhole
+    camera's (here: shuffled within the image), taps fall outside the staged box and every such thread must take the
+    direct-sampling fallback: results stay exact."""
+    d = dev()
+    from ml_gmpi_b200 import synth
+    case = synth.make_case(n_planes=12, tex=96, img=200, n_mpi=1, views_per_mpi=2, seed=3, device=d)   # 200 = partial tiles
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    perm = torch.randperm(200 * 200, generator=gen).to(d)
+    ray = case.ray_dir.reshape(2, 3, -1)[:, :, perm].reshape(2, 3, 200, 200).contiguous()
+    color, depth = g.render_views(case.rgba, case.dhw, case.view2mpi, ray, case.eye, case.z_dir)
+    n = lambda t: t.cpu().numpy()
+    rc, rd, _ = mpi_oracle.forward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(ray), n(case.eye), n(case.z_dir), nthreads=16)
+    assert rel_err(n(color), rc) <= EXPECT and rel_err(n(depth), rd) <= EXPECT
+
+
+def test_degenerate_rays_do_not_poison_neighbours(fwd_variant):
+    """ray_z == 0 (ray parallel to the planes) makes scale inf/NaN for that pixel only."""
+    d = dev()
+    from ml_gmpi_b200 import synth
+    case = synth.make_case(n_planes=8, tex=64, img=64, n_mpi=1, seed=4, device=d)
+    ray = case.ray_dir.clone()
+    ray[0, 2, 10, 10:14] = 0.0
+    ray[0, :, 20, 20] = float("nan")
+    color, depth = g.render_views(case.rgba, case.dhw, case.view2mpi, ray, case.eye, case.z_dir)
+    n = lambda t: t.cpu().numpy()
+    rc, rd, _ = mpi_oracle.forward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(ray), n(case.eye), n(case.z_dir))
+    ok = np.ones((64, 64), bool); ok[10, 10:14] = False; ok[20, 20] = False
+    assert rel_err(n(color)[0][:, ok], rc[0][:, ok]) <= EXPECT
+    assert np.all(n(color)[0][:, 10, 10:14] == 0) and np.all(rc[0][:, 10, 10:14] == 0)
