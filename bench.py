@@ -56,7 +56,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -65,9 +65,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -77,7 +77,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        inside = [r for (ts, r) in self.rows if t0 is not None and t0 <= ts <= t1 + 0.03]
+        window = "timed region"
+        if not inside:      # timed region shorter than the sampling period: use everything since warm-up started
+            inside, window = [r for (_, r) in self.rows], "warm-up + timed region"
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -86,7 +90,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -207,19 +211,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     assert int(flags.item()) == 0, f"render flagged {int(flags.item())} on the synthetic workload"
 
     # --- timed region: whole step (render [+ all-gather]), CUDA events, max over ranks ---------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     launches[0] = 0
+    t_wall0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
         kev[i][0].record(stream)
@@ -230,7 +235,8 @@ def main():
             dist.all_gather_into_tensor(frames_all, frames_local)
     ev[1].record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[1])
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     n_launch = launches[0]

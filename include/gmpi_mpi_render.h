@@ -114,6 +114,11 @@ int gmpi_debug_plane_coords(const int32_t* view2mpi, const float* dhw, const flo
                             const float* eye, float* out, int V, int N, int Ht, int Wt, int H,
                             int W, uint32_t options, void* stream);
 
+/* Test hook: same as gmpi_debug_plane_coords through the staged kernel's packed (f32x2) coordinate code (H*W even). */
+int gmpi_debug_plane_coords_packed(const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                                   const float* eye, float* out, int V, int N, int Ht, int Wt, int H,
+                                   int W, uint32_t options, void* stream);
+
 /* Test hook: force the forward kernel variant: 0 auto (default), 1 direct-gather, 2 TMA-staged. */
 int gmpi_debug_set_fwd_variant(int variant);
 

@@ -21,7 +21,7 @@ ABI_VERSION = 1
 
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
-    "gmpi_mpi_render_bwd", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant",
+    "gmpi_mpi_render_bwd", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed",
 ]
 
 _lib = None
@@ -35,11 +35,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("GMPI_LIB_PATH", LIB_PATH)     # override: A/B-testing kernel builds
+    if not os.path.exists(path):
         raise GmpiLibraryError(
-            f"{LIB_PATH} is missing: the CUDA (sm_100a) renderer is not built. Run "
+            f"{path} is missing: the CUDA (sm_100a) renderer is not built. Run "
             "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     vp, i, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32
     lib.gmpi_abi_version.restype = i
     lib.gmpi_abi_version.argtypes = []
@@ -57,6 +58,8 @@ def load():
     lib.gmpi_mpi_render_fwd_host.argtypes = [vp] * 9 + [i] * 7 + [u32, i]
     lib.gmpi_debug_plane_coords.restype = i
     lib.gmpi_debug_plane_coords.argtypes = [vp] * 5 + [i] * 6 + [u32, vp]
+    lib.gmpi_debug_plane_coords_packed.restype = i
+    lib.gmpi_debug_plane_coords_packed.argtypes = [vp] * 5 + [i] * 6 + [u32, vp]
     lib.gmpi_debug_division.restype = i
     lib.gmpi_debug_division.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.gmpi_debug_set_fwd_variant.restype = i

@@ -14,15 +14,22 @@
 
 namespace gmpi {
 
-constexpr int kTileW = 64, kTileH = 32;
-constexpr int kConsWarps = 16, kConsThreads = kConsWarps * 32, kStagedThreads = kConsThreads + 32;
+#ifndef GMPI_CONS_WARPS
+#define GMPI_CONS_WARPS 15   // 15 consumer warps + producer = 16 warps = 4 per scheduler, 128 registers per thread
+#endif
+constexpr int kTileW = 64, kTileH = 2 * GMPI_CONS_WARPS;
+constexpr int kConsWarps = GMPI_CONS_WARPS, kConsThreads = kConsWarps * 32, kStagedThreads = kConsThreads + 32;
 constexpr int kStages = 3;
 constexpr int kRowsPerOp = 4;
-constexpr int kMaxBW = 80, kMaxBH = 44;                 // largest staged footprint (texels)
-constexpr int kMinBW = 40, kBWStep = 8;   // multiples of 8: row pitch 4*bw = 0 mod 32 banks
+constexpr int kMaxBW = 88;
+constexpr int kMaxBH = (((kTileH * 5) / 4 + 6 + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp;   // footprint rows at scale 1.25 + taps/slack, whole chunks                 // largest staged footprint (texels)
+// Box widths are compile-time classes (multiples of 8: row pitch 4*bw = 0 mod 32 banks) so that the consumers'
+// sixteen taps are LDS [reg + immediate]; the producer picks the narrowest class that covers the footprint.
+constexpr int kMinBW = 56, kBWStep = 8;
 constexpr int kNumMaps = (kMaxBW - kMinBW) / kBWStep + 1;
+constexpr int kMaxPlanesStaged = 512;                  // plane-constant table: 32 B per plane in shared memory
 constexpr int kStageFloats = kMaxBW * kMaxBH * 4;
-constexpr size_t kStagedSmem = (size_t)kStages * kStageFloats * 4;
+constexpr size_t kStagedSmem = (size_t)kStages * kStageFloats * 4 + (size_t)kMaxPlanesStaged * 32;
 
 struct TmaMaps {
     CUtensorMap m[kNumMaps];
@@ -31,12 +38,124 @@ struct TmaMaps {
 // per-stage header written by the producer before it arms the full barrier
 struct __align__(16) StageMeta {
     float fbx0, fby0;      // box origin (texel coordinates of smem element [0][.][0]) as floats
-    float fbw2, fbh2;      // bw-2, rows-2: a footprint with north-west tap (rx, ry) fits iff 0<=rx<=bw-2, 0<=ry<=rows-2
-    int bw;                // staged width (row pitch = 4*bw floats)
-    int mode;              // 0 staged, 1 nothing to sample (footprint misses the texture), 2 sample global memory directly
-    int pad0, pad1;
-    PlaneConst pc;
+    int rows2;             // staged rows - 2: a footprint with north-west tap (rx, ry) fits iff 0<=rx<=bw-2, 0<=ry<=rows-2
+    int bw_mode;           // staged width (row pitch = 4*bw floats) | mode << 16;
+                           // mode 0 staged, 1 nothing to sample (footprint misses the texture), 2 sample global memory directly
 };
+
+// ---- packed dual-fp32 arithmetic (sm_100 FFMA2/FADD2/FMUL2): one issue slot for two pixels, IEEE rn per element ----
+typedef float2 f2;
+__device__ __forceinline__ f2 splat(float a) { return make_float2(a, a); }
+// Inline PTX, not the __fmul2_rn/__fadd2_rn intrinsics: the compiler contracts those into one FFMA2 (observed: texel
+// coordinates off by a few ulp), which breaks the reference's separately rounded mul-then-add.  asm blocks cannot be fused.
+__device__ __forceinline__ unsigned long long f2_bits(f2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ f2 bits_f2(unsigned long long v) { return *reinterpret_cast<f2*>(&v); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(r);
+}
+// a / b correctly rounded with y = RN(1/b), nb = -b (div_by_rcp, two pixels at once)
+__device__ __forceinline__ f2 div2_by_rcp(f2 a, f2 nb, f2 y) {
+    const f2 q0 = mul2(a, y);
+    const f2 r = fma2(q0, nb, a);
+    return fma2(r, y, q0);
+}
+
+// A thread's four pixels as two pairs: pair P = (x = lane, x = lane + 32) on tile row 2*warp + P.
+struct RayPairs {
+    f2 rx2[2], ry2[2];   // 2*ray_x, 2*ray_y
+    f2 nrz[2], yrz[2];   // -ray_z, RN(1/ray_z)
+};
+struct CoordPairs {
+    f2 ix[2], iy[2], sc[2];
+};
+
+// Texel coordinates on one plane, exact-division fast form; op order of plane_coord (mpi.py:74-90 + unnormalize).
+template <bool kAlignCorners>
+__device__ __forceinline__ void coords_pairs(const PlaneConst& pc, const RayPairs& rp, f2 ex2, f2 ey2, f2 hsx, f2 hsy, float fWt,
+                                             float fHt, CoordPairs& c) {
+    const f2 zd = splat(pc.z_diff), ypw = splat(pc.ypw), yph = splat(pc.yph), npw = splat(-pc.pw), nph = splat(-pc.ph);
+    const f2 one = splat(1.0f);
+#pragma unroll
+    for (int P = 0; P < 2; ++P) {
+        const f2 sq = div2_by_rcp(zd, rp.nrz[P], rp.yrz[P]);                 // scale = z_diff / ray_z
+        // 2*(e_x + ray_x*scale): mul, THEN add (two roundings, mpi.py:79).  Scalar on purpose: ptxas fuses
+        // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS even with --fmad=false), which is not the reference's
+        // arithmetic; the scalar __fmul_rn/__fadd_rn intrinsics are never contracted.
+        const f2 X2 = make_float2(__fadd_rn(ex2.x, __fmul_rn(rp.rx2[P].x, sq.x)), __fadd_rn(ex2.y, __fmul_rn(rp.rx2[P].y, sq.y)));
+        const f2 Y2 = make_float2(__fadd_rn(ey2.x, __fmul_rn(rp.ry2[P].x, sq.x)), __fadd_rn(ey2.y, __fmul_rn(rp.ry2[P].y, sq.y)));
+        f2 u = div2_by_rcp(X2, npw, ypw);                                    // (2x) / width
+        f2 v = div2_by_rcp(Y2, nph, yph);
+        if (kAlignCorners) {
+            c.ix[P] = mul2(add2(u, one), hsx);                               // (u+1) * ((Wt-1)/2)
+            c.iy[P] = mul2(add2(v, one), hsy);
+        } else {
+            if (u.x >= -1.0f && u.x <= 1.0f) u.x = __fmul_rn(u.x, 0.95f);
+            if (u.y >= -1.0f && u.y <= 1.0f) u.y = __fmul_rn(u.y, 0.95f);
+            if (v.x >= -1.0f && v.x <= 1.0f) v.x = __fmul_rn(v.x, 0.95f);
+            if (v.y >= -1.0f && v.y <= 1.0f) v.y = __fmul_rn(v.y, 0.95f);
+            const f2 half = splat(0.5f), m1 = splat(-1.0f);
+            c.ix[P] = mul2(add2(mul2(add2(u, one), splat(fWt)), m1), half);  // ((u+1)*W - 1) / 2
+            c.iy[P] = mul2(add2(mul2(add2(v, one), splat(fHt)), m1), half);
+        }
+        c.sc[P] = sq;
+    }
+}
+
+// Sample + composite the four pixels from a staged box of compile-time width BW.  Returns false (and changes nothing)
+// if any of the four footprints is not inside the box.
+template <int BW>
+__device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float fbx0, float fby0, int rows2, const CoordPairs& c,
+                                             f2 (&T)[2], f2 (&cr)[2], f2 (&cg)[2], f2 (&cb)[2], f2 (&cws)[2]) {
+    const f2 m1 = splat(-1.0f), one = splat(1.0f), nbx = splat(-fbx0), nby = splat(-fby0);
+    f2 fx0[2], fy0[2];
+    int ia[2], ib[2];
+    bool inbox = true;
+#pragma unroll
+    for (int P = 0; P < 2; ++P) {
+        fx0[P] = make_float2(floorf(c.ix[P].x), floorf(c.ix[P].y));
+        fy0[P] = make_float2(floorf(c.iy[P].x), floorf(c.iy[P].y));
+        const f2 rx = add2(fx0[P], nbx), ry = add2(fy0[P], nby);     // exact (integers); saturate and fail the test when far away
+        const int rxa = (int)rx.x, rxb = (int)rx.y, rya = (int)ry.x, ryb = (int)ry.y;
+        inbox = inbox && (unsigned)rxa <= (unsigned)(BW - 2) && (unsigned)rxb <= (unsigned)(BW - 2) &&
+                (unsigned)rya <= (unsigned)rows2 && (unsigned)ryb <= (unsigned)rows2;
+        ia[P] = rya * (4 * BW) + rxa;                                 // [row][channel][x], compile-time pitch
+        ib[P] = ryb * (4 * BW) + rxb;
+    }
+    if (!inbox) return false;
+#pragma unroll
+    for (int P = 0; P < 2; ++P) {
+        const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);   // fractional parts (exact)
+        const f2 wy0 = fma2(wy1, m1, one);
+        const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
+        const float* ta = sb + ia[P];
+        const float* tb = sb + ib[P];
+#define GMPI_TAP(ch)                                                                                           \
+    fma2(make_float2(ta[(4 + ch) * BW + 1], tb[(4 + ch) * BW + 1]), w11,                                       \
+         fma2(make_float2(ta[(4 + ch) * BW], tb[(4 + ch) * BW]), w10,                                          \
+              fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
+        const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2), a = GMPI_TAP(3);
+#undef GMPI_TAP
+        const f2 w = mul2(a, T[P]);                     // mpi.py:423
+        cr[P] = fma2(w, r, cr[P]);                      // mpi.py:430
+        cg[P] = fma2(w, g, cg[P]);
+        cb[P] = fma2(w, b, cb[P]);
+        cws[P] = fma2(w, c.sc[P], cws[P]);              // depth_i = scale * (ray . z_dir), mpi.py:150
+        T[P] = fma2(w, m1, T[P]);   // T(1-a); the reference's +1e-10 changes any later weight by < 1e-10 absolute
+    }
+    return true;
+}
 
 // Rare path (a ray whose footprint is not in the staged box): sample the plane from global memory.  Out of line so
 // that it does not cost registers in the hot loop.
@@ -46,11 +165,14 @@ __device__ __noinline__ float4 sample_plane_direct(const float* __restrict__ pla
     return make_float4(tap4(plane, tp), tap4(plane + tex, tp), tap4(plane + 2 * tex, tp), tap4(plane + 3 * tex, tp));
 }
 
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
+
 template <bool kAlignCorners>
 __global__ void __launch_bounds__(kStagedThreads, 1)
 mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_buf = reinterpret_cast<float*>(smem_raw);   // the ring starts the dynamic segment (1024-byte aligned)
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kStageFloats * 4);   // [N] of the current view
     __shared__ StageMeta s_meta[kStages];
     __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
 
@@ -82,7 +204,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             const float* e = p.eye + 3 * v;
             const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
             const float zd[3] = {0.f, 0.f, 1.f};
-            // lanes 0..3 (replicated over the warp): the four corner pixels of the tile, clamped into the image
+            // the four corner pixels of the tile (replicated over the warp), clamped into the image
             const int cx = min(px0 + ((lane & 1) ? kTileW - 1 : 0), p.W - 1);
             const int cy = min(py0 + ((lane & 2) ? kTileH - 1 : 0), p.H - 1);
             const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)cy * p.W + cx;
@@ -99,10 +221,11 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 const int fx = finite ? (int)floorf(tc.ix) : 0, fy = finite ? (int)floorf(tc.iy) : 0;
                 const int xmin = __reduce_min_sync(0xffffffffu, fx), xmax = __reduce_max_sync(0xffffffffu, fx);
                 const int ymin = __reduce_min_sync(0xffffffffu, fy), ymax = __reduce_max_sync(0xffffffffu, fy);
-                const int bx0 = xmin - 1, by0 = ymin - 1;
-                const int need_w = xmax - xmin + 4, need_h = ymax - ymin + 4;     // +1 east/south tap, +-1 slack
+                // TMA needs a 16-byte aligned start in the innermost dimension: the box origin is a multiple of 4 texels
+                const int bx0 = ((xmin - 1) >> 2) << 2, by0 = ymin - 1;
+                const int need_w = xmax - bx0 + 3, need_h = ymax - ymin + 4;      // +1 east/south tap, +-1 slack
                 int mode = 0;
-                if (!all_finite || need_w > kMaxBW || need_h > kMaxBH) mode = 2;
+                if (!all_finite || need_w > kMaxBW || ((need_h + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp > kMaxBH) mode = 2;   // would not fit a ring stage
                 else if (bx0 > Wt - 1 || bx0 + need_w - 1 < 0 || by0 > Ht - 1 || by0 + need_h - 1 < 0) mode = 1;
                 const int k = mode == 0 ? max(0, (need_w - kMinBW + kBWStep - 1) / kBWStep) : 0;
                 const int bw = kMinBW + k * kBWStep;
@@ -112,9 +235,8 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 if (lane == 0) {
                     StageMeta mt;
                     mt.fbx0 = (float)bx0; mt.fby0 = (float)by0;
-                    mt.fbw2 = (float)(bw - 2); mt.fbh2 = (float)(rows - 2);
-                    mt.bw = bw; mt.mode = mode; mt.pad0 = mt.pad1 = 0;
-                    mt.pc = pc;
+                    mt.rows2 = rows - 2;
+                    mt.bw_mode = bw | (mode << 16);
                     s_meta[s] = mt;
                     if (n_ops > 0) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16));
                     else mbar_arrive(&s_full[s]);
@@ -139,6 +261,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 if (!(__ldg(p.dhw + (size_t)j * 3) >= eye0_z)) flag |= GMPI_FLAG_PLANE_BEHIND_EYE;
         }
         const size_t tex = (size_t)Ht * Wt;
+        int v_table = -1;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int v = t / tiles_per_view, tt = t - v * tiles_per_view;
             const int px0 = (tt % tiles_x) * kTileW, py0 = (tt / tiles_x) * kTileH;
@@ -146,10 +269,16 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             const float* e = p.eye + 3 * v;
             const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
             const float zd[3] = {__ldg(p.z_dir + 3 * v), __ldg(p.z_dir + 3 * v + 1), __ldg(p.z_dir + 3 * v + 2)};
+            if (v != v_table) {          // (view, plane) constants, once per view and CTA
+                consumer_bar_sync();     // everyone is done with the previous view's table
+                for (int i = threadIdx.x; i < N; i += kConsThreads) s_pc[i] = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
+                consumer_bar_sync();
+                v_table = v;
+            }
             const float* rays = p.ray_dir + (size_t)v * 3 * img;
-            RayConst rc[4];
-            bool rays_fast = in_safe_range(ev[0]) || ev[0] == 0.0f;
-            rays_fast = rays_fast && (in_safe_range(ev[1]) || ev[1] == 0.0f);
+            RayConst rc[4];      // scalar copies, only for the generic (rare) body and the epilogue
+            RayPairs rp;
+            bool rays_fast = (in_safe_range(ev[0]) || ev[0] == 0.0f) && (in_safe_range(ev[1]) || ev[1] == 0.0f);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int px = min(px0 + lane + 32 * (q & 1), p.W - 1), py = min(py0 + 2 * warp + (q >> 1), p.H - 1);
@@ -157,79 +286,65 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 rc[q] = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
                 rays_fast = rays_fast && rc[q].fast && fabsf(rc[q].rx2) <= 0x1p40f && fabsf(rc[q].ry2) <= 0x1p40f;
             }
-            // warp-uniform: every ray of this warp is in the range where the reciprocal+FMA division is exact and
-            // no coordinate can be NaN, so the per-plane body needs no per-pixel range checks
+#pragma unroll
+            for (int P = 0; P < 2; ++P) {
+                rp.rx2[P] = make_float2(rc[2 * P].rx2, rc[2 * P + 1].rx2);
+                rp.ry2[P] = make_float2(rc[2 * P].ry2, rc[2 * P + 1].ry2);
+                rp.nrz[P] = make_float2(-rc[2 * P].rz, -rc[2 * P + 1].rz);
+                rp.yrz[P] = make_float2(rc[2 * P].yrz, rc[2 * P + 1].yrz);
+            }
+            const f2 ex2 = splat(rc[0].ex2), ey2 = splat(rc[0].ey2), hsx2 = splat(hsx), hsy2 = splat(hsy);
+            // warp-uniform: every ray of this warp is in the range where the reciprocal+FMA division is exact and no
+            // coordinate can be NaN, so the per-plane body needs no per-pixel range checks
             const bool warp_fast = __all_sync(0xffffffffu, rays_fast);
-            float T[4] = {1.f, 1.f, 1.f, 1.f}, cr[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f},
-                  cb[4] = {0.f, 0.f, 0.f, 0.f}, cws[4] = {0.f, 0.f, 0.f, 0.f};
+            f2 T[2] = {splat(1.f), splat(1.f)}, cr[2] = {splat(0.f), splat(0.f)}, cg[2] = {splat(0.f), splat(0.f)},
+               cb[2] = {splat(0.f), splat(0.f)}, cws[2] = {splat(0.f), splat(0.f)};
             const float* plane = p.rgba + (size_t)m * N * 4 * tex;
+            // software pipeline: the coordinates of plane i+1 are computed while plane i's taps are in flight
+            CoordPairs cn;
+            PlaneConst pcn = s_pc[0];
+            bool fast_n = warp_fast && pcn.fast != 0.0f;
+            if (fast_n) coords_pairs<kAlignCorners>(pcn, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cn);
             for (int i = 0; i < N; ++i, ++it, plane += 4 * tex) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
+                const CoordPairs cc = cn;
+                const PlaneConst pcc = pcn;
+                const bool fast_c = fast_n;
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloats;
-                const int bw = mt.bw, bw4 = 4 * mt.bw;
+                const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
                 bool done = false;
-                if (warp_fast && mt.pc.fast != 0.0f && mt.mode == 0) {
-                    // ---- fast body: straight-line code for the four pixels ----
-                    float ix[4], iy[4], sc[4], fx0[4], fy0[4], rx[4], ry[4];
-                    bool inbox = true;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float sq = div_by_rcp(mt.pc.z_diff, rc[q].rz, rc[q].yrz);
-                        const float X2 = __fadd_rn(rc[q].ex2, __fmul_rn(rc[q].rx2, sq));
-                        const float Y2 = __fadd_rn(rc[q].ey2, __fmul_rn(rc[q].ry2, sq));
-                        float u = div_by_rcp(X2, mt.pc.pw, mt.pc.ypw);
-                        float vv = div_by_rcp(Y2, mt.pc.ph, mt.pc.yph);
-                        if (kAlignCorners) {
-                            ix[q] = __fmul_rn(__fadd_rn(u, 1.0f), hsx);
-                            iy[q] = __fmul_rn(__fadd_rn(vv, 1.0f), hsy);
-                        } else {
-                            if (u >= -1.0f && u <= 1.0f) u = __fmul_rn(u, 0.95f);
-                            if (vv >= -1.0f && vv <= 1.0f) vv = __fmul_rn(vv, 0.95f);
-                            ix[q] = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(u, 1.0f), fWt), -1.0f), 0.5f);
-                            iy[q] = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(vv, 1.0f), fHt), -1.0f), 0.5f);
-                        }
-                        sc[q] = sq;
-                        fx0[q] = floorf(ix[q]); fy0[q] = floorf(iy[q]);
-                        rx[q] = fx0[q] - mt.fbx0; ry[q] = fy0[q] - mt.fby0;
-                        inbox = inbox && rx[q] >= 0.0f && rx[q] <= mt.fbw2 && ry[q] >= 0.0f && ry[q] <= mt.fbh2;
-                    }
-                    if (inbox) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float wx1 = ix[q] - fx0[q], wy1 = iy[q] - fy0[q];
-                            const float wy0 = 1.0f - wy1;
-                            const float w11 = wx1 * wy1, w10 = wy1 - w11, w01 = wx1 - w11, w00 = wy0 - w01;
-                            const float* t0 = sb + ((int)ry[q] * bw4 + (int)rx[q]);     // [row][channel][x]
-                            const float* t1 = t0 + bw4;
-                            const float r = fmaf(t1[1], w11, fmaf(t1[0], w10, fmaf(t0[1], w01, t0[0] * w00)));
-                            t0 += bw; t1 += bw;
-                            const float g = fmaf(t1[1], w11, fmaf(t1[0], w10, fmaf(t0[1], w01, t0[0] * w00)));
-                            t0 += bw; t1 += bw;
-                            const float b = fmaf(t1[1], w11, fmaf(t1[0], w10, fmaf(t0[1], w01, t0[0] * w00)));
-                            t0 += bw; t1 += bw;
-                            const float a = fmaf(t1[1], w11, fmaf(t1[0], w10, fmaf(t0[1], w01, t0[0] * w00)));
-                            const float w = a * T[q];                       // mpi.py:423
-                            cr[q] = fmaf(w, r, cr[q]);                      // mpi.py:430
-                            cg[q] = fmaf(w, g, cg[q]);
-                            cb[q] = fmaf(w, b, cb[q]);
-                            cws[q] = fmaf(w, sc[q], cws[q]);                // depth_i = scale * (ray . z_dir), mpi.py:150
-                            T[q] -= w;   // T(1-a); the reference's +1e-10 changes any later weight by < 1e-10 absolute
-                        }
-                        done = true;
+                if (fast_c && mode == 0) {
+                    switch (bw) {   // warp-uniform
+                        case 56: done = sample_pairs<56>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
+                        case 64: done = sample_pairs<64>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
+                        case 72: done = sample_pairs<72>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
+                        case 80: done = sample_pairs<80>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
+                        default: done = sample_pairs<88>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                     }
                 }
+                // next plane's constants and coordinates (independent of the staged data)
+                pcn = s_pc[min(i + 1, N - 1)];
+                fast_n = warp_fast && pcn.fast != 0.0f;
+                if (fast_n) coords_pairs<kAlignCorners>(pcn, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cn);
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----
+                    const int bw4 = 4 * bw;
+                    const float fbw2 = (float)(bw - 2), fbh2 = (float)mt.rows2;
+                    float* Ts = reinterpret_cast<float*>(T);
+                    float* crs = reinterpret_cast<float*>(cr);
+                    float* cgs = reinterpret_cast<float*>(cg);
+                    float* cbs = reinterpret_cast<float*>(cb);
+                    float* cwss = reinterpret_cast<float*>(cws);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const TexCoord tc = plane_coord<kAlignCorners>(mt.pc, rc[q], hsx, hsy, fWt, fHt);
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);
                         const float rxx = fx - mt.fbx0, ryy = fy - mt.fby0;
                         float r, g, b, a;
-                        if (mt.mode == 0 && rxx >= 0.0f && rxx <= mt.fbw2 && ryy >= 0.0f && ryy <= mt.fbh2) {
+                        if (mode == 0 && rxx >= 0.0f && rxx <= fbw2 && ryy >= 0.0f && ryy <= fbh2) {
                             const float wx1 = tc.ix - fx, wy1 = tc.iy - fy;
                             const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
                             const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
@@ -239,18 +354,18 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                             g = fmaf(t1[bw + 1], w11, fmaf(t1[bw], w10, fmaf(t0[bw + 1], w01, t0[bw] * w00)));
                             b = fmaf(t1[2 * bw + 1], w11, fmaf(t1[2 * bw], w10, fmaf(t0[2 * bw + 1], w01, t0[2 * bw] * w00)));
                             a = fmaf(t1[3 * bw + 1], w11, fmaf(t1[3 * bw], w10, fmaf(t0[3 * bw + 1], w01, t0[3 * bw] * w00)));
-                        } else if (mt.mode != 1 && coord_hits(tc.ix, tc.iy, fWt, fHt)) {
+                        } else if (mode != 1 && coord_hits(tc.ix, tc.iy, fWt, fHt)) {
                             const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
                             r = sv.x; g = sv.y; b = sv.z; a = sv.w;
                         } else {
                             continue;   // no texel under this ray on this plane: contributes exactly nothing
                         }
-                        const float w = a * T[q];
-                        cr[q] = fmaf(w, r, cr[q]);
-                        cg[q] = fmaf(w, g, cg[q]);
-                        cb[q] = fmaf(w, b, cb[q]);
-                        cws[q] = fmaf(w, tc.scale, cws[q]);
-                        T[q] -= w;
+                        const float w = a * Ts[q];
+                        crs[q] = fmaf(w, r, crs[q]);
+                        cgs[q] = fmaf(w, g, cgs[q]);
+                        cbs[q] = fmaf(w, b, cbs[q]);
+                        cwss[q] = fmaf(w, tc.scale, cwss[q]);
+                        Ts[q] -= w;
                     }
                 }
                 __syncwarp();
@@ -258,7 +373,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 if (check_last && i == N - 1) {     // assert_not_out_of_last_plane, mpi.py:103-109 (once per tile)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const TexCoord tc = plane_coord<kAlignCorners>(mt.pc, rc[q], hsx, hsy, fWt, fHt);
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
                         if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
                     }
                 }
@@ -268,13 +383,15 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 const int px = px0 + lane + 32 * (q & 1), py = py0 + 2 * warp + (q >> 1);
                 if (px >= p.W || py >= p.H) continue;
                 const size_t pix = (size_t)py * p.W + px;
-                float o0 = cr[q], o1 = cg[q], o2 = cb[q];
+                float o0 = (q & 1) ? cr[q >> 1].y : cr[q >> 1].x, o1 = (q & 1) ? cg[q >> 1].y : cg[q >> 1].x;
+                float o2 = (q & 1) ? cb[q >> 1].y : cb[q >> 1].x;
+                const float ws = (q & 1) ? cws[q >> 1].y : cws[q >> 1].x;
                 if (minus1_1) {
                     o0 = fmaf(2.0f, o0, -1.0f); o1 = fmaf(2.0f, o1, -1.0f); o2 = fmaf(2.0f, o2, -1.0f);
                 }
                 float* co = p.color + (size_t)v * 3 * img + pix;
                 co[0] = o0; co[img] = o1; co[2 * img] = o2;
-                p.depth[(size_t)v * img + pix] = cws[q] * rc[q].dz;
+                p.depth[(size_t)v * img + pix] = ws * rc[q].dz;
             }
         }
         if (flag) atomicOr(p.flags, flag);

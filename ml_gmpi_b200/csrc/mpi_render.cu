@@ -270,6 +270,38 @@ __global__ void mpi_debug_coords_kernel(const int32_t* view2mpi, const float* dh
     }
 }
 
+// Test hook for the packed (f32x2) coordinate path of the staged kernel: pixels 2k, 2k+1 of a row form a pair.
+template <bool kAlignCorners>
+__global__ void mpi_debug_coords_packed_kernel(const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                                               const float* eye, float* out, int V, int N, int Ht, int Wt, int H, int W) {
+    const size_t img = (size_t)H * W;
+    const size_t pair = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (pair * 2 + 1 >= img) return;
+    const int m = view2mpi[v];
+    const float* e = eye + 3 * v;
+    const float ev[3] = {e[0], e[1], e[2]};
+    const float zd[3] = {0.f, 0.f, 1.f};
+    RayConst rc[2];
+    for (int k = 0; k < 2; ++k) {
+        const float* rd = ray_dir + (size_t)v * 3 * img + pair * 2 + k;
+        rc[k] = make_ray_const(rd[0], rd[img], rd[2 * img], ev, zd);
+    }
+    RayPairs rp;
+    for (int P = 0; P < 2; ++P) {
+        rp.rx2[P] = make_float2(rc[0].rx2, rc[1].rx2); rp.ry2[P] = make_float2(rc[0].ry2, rc[1].ry2);
+        rp.nrz[P] = make_float2(-rc[0].rz, -rc[1].rz); rp.yrz[P] = make_float2(rc[0].yrz, rc[1].yrz);
+    }
+    const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    for (int i = 0; i < N; ++i) {
+        const PlaneConst pc = make_plane_const(dhw + ((size_t)m * N + i) * 3, ev[2]);
+        CoordPairs c;
+        coords_pairs<kAlignCorners>(pc, rp, splat(rc[0].ex2), splat(rc[0].ey2), splat(hsx), splat(hsy), (float)Wt, (float)Ht, c);
+        float* o = out + (((size_t)v * N + i) * 2) * img + pair * 2;
+        o[0] = c.ix[0].x; o[1] = c.ix[0].y; o[img] = c.iy[0].x; o[img + 1] = c.iy[0].y;
+    }
+}
+
 __global__ void mpi_debug_division_kernel(const float* a, const float* b, float* out_fast, float* out_ieee, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float x = a[i], y = b[i];
@@ -312,8 +344,9 @@ int gmpi_debug_set_fwd_variant(int variant) {
 }
 
 // staged needs 16-byte row strides for the tensor map and enough tiles to fill the persistent grid
-static bool staged_eligible(int V, int Ht, int Wt, int H, int W) {
+static bool staged_eligible(int V, int N, int Ht, int Wt, int H, int W) {
     (void)Ht;
+    if (N > kMaxPlanesStaged) return false;
     if (Wt % 4 != 0) return false;
     if (g_fwd_variant == 2) return true;
     if (g_fwd_variant == 1) return false;
@@ -322,8 +355,7 @@ static bool staged_eligible(int V, int Ht, int Wt, int H, int W) {
 }
 
 const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
-    (void)N;
-    return staged_eligible(1 << 20, Ht, Wt, H, W) ? "fwd_staged_tma_64x32" : "fwd_direct_32x8";
+    return staged_eligible(1 << 20, N, Ht, Wt, H, W) ? "fwd_staged_tma_64x32" : "fwd_direct_32x8";
 }
 
 int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
@@ -338,7 +370,7 @@ int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float*
     p.color = color; p.depth = depth; p.flags = flags;
     p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
     cudaStream_t st = (cudaStream_t)stream;
-    if (staged_eligible(V, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)) {
+    if (staged_eligible(V, N, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)) {
         TmaMaps maps;
         bool ok = true;
         for (int k = 0; k < kNumMaps && ok; ++k)
@@ -447,6 +479,21 @@ int gmpi_debug_plane_coords(const int32_t* view2mpi, const float* dhw, const flo
         mpi_debug_coords_kernel<true><<<grid, 256, 0, st>>>(view2mpi, dhw, ray_dir, eye, out, V, N, Ht, Wt, H, W);
     else
         mpi_debug_coords_kernel<false><<<grid, 256, 0, st>>>(view2mpi, dhw, ray_dir, eye, out, V, N, Ht, Wt, H, W);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_debug_plane_coords_packed(const int32_t* view2mpi, const float* dhw, const float* ray_dir, const float* eye,
+                                   float* out, int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
+    if (!view2mpi || !dhw || !ray_dir || !eye || !out) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (V < 1 || N < 1 || Ht < 1 || Wt < 1 || H < 1 || W < 1 || ((size_t)H * W) % 2) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pairs = (size_t)H * W / 2;
+    dim3 grid((unsigned)((pairs + 255) / 256), V);
+    if (options & GMPI_ALIGN_CORNERS)
+        mpi_debug_coords_packed_kernel<true><<<grid, 256, 0, st>>>(view2mpi, dhw, ray_dir, eye, out, V, N, Ht, Wt, H, W);
+    else
+        mpi_debug_coords_packed_kernel<false><<<grid, 256, 0, st>>>(view2mpi, dhw, ray_dir, eye, out, V, N, Ht, Wt, H, W);
     GMPI_CUDA_OK(cudaGetLastError());
     return GMPI_OK;
 }

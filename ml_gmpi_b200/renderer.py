@@ -1,0 +1,132 @@
+"""Mirror of the reference's renderer façade, `gmpi.core.mpi_renderer.MPIRenderer` (gmpi/core/mpi_renderer.py:21-469),
+for the render path only: plane geometry (`:105-152`), camera (`:80-103`), pose sampling (`:337-385`) and `render`
+(`:387-469`).  Same constructor keywords, same `render` signature and return values
+`(img in [-1,1] [V,3,H,W], depth [V,1,H,W], c2w [V,4,4], angles [V,2] = (pitch, yaw))`.
+
+Differences, all on the fast side:
+  * the rgba range assert (`:447-449`: torch.min + torch.max = two HBM passes + two syncs), the alpha assert of
+    MPI.check_shapes and the geometric asserts are evaluated on the device and raised after one sync;
+  * `2*color-1` (`:467`) is fused into the render kernel's store;
+  * rays for all views are generated in one batched matmul instead of a Python loop (`:370-376`);
+  * the 10 001-pose envelope of the constructor is vectorised (7.7 s -> ~10 ms).
+The generator-side helpers `get_xyz*` (`:154-318`) are not part of the render path and stay in the reference.
+"""
+import logging
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .camera import PinholeCamera, focal_from_fov, sample_yaw_pitch, sphere_poses
+from .geometry import plane_dhw_table
+from .mpi import MPI, check_range, render_views
+
+logger = logging.getLogger("ml_gmpi_b200")
+
+
+class MPIRenderer:
+    def __init__(self, *, n_mpi_planes, plane_min_d, plane_max_d, plan_spatial_enlarge_factor, plane_distances_sample_method,
+                 cam_fov, sphere_center_z, sphere_r, horizontal_mean, horizontal_std, vertical_mean, vertical_std,
+                 cam_pose_n_truncated_stds, cam_sample_method, mpi_align_corners=True, use_xyz_ztype="depth",
+                 use_normalized_xyz=False, normalized_xyz_range="-11", use_confined_volume=False,
+                 device=torch.device("cpu"), validate: str = "full"):
+        self.mpi = MPI(align_corners=mpi_align_corners, validate=validate)
+        self.validate = validate
+        self.use_confined_volume = use_confined_volume
+        self.n_mpi_planes = n_mpi_planes
+        self.plane_min_d, self.plane_max_d = plane_min_d, plane_max_d
+        self.plan_spatial_enlarge_factor = plan_spatial_enlarge_factor
+        self.plane_distances_sample_method = plane_distances_sample_method
+        self.cam_fov = cam_fov
+        self.sphere_center = np.array([0, 0, sphere_center_z])
+        self.sphere_r = sphere_r
+        self.horizontal_mean, self.horizontal_std = horizontal_mean, horizontal_std
+        self.vertical_mean, self.vertical_std = vertical_mean, vertical_std
+        self.cam_pose_n_truncated_stds = cam_pose_n_truncated_stds
+        self.cam_sample_method = cam_sample_method
+        self.device = torch.device(device)
+        self.use_xyz_ztype, self.use_normalized_xyz, self.normalized_xyz_range = use_xyz_ztype, use_normalized_xyz, normalized_xyz_range
+        assert self.normalized_xyz_range in ["01", "-11"], f"{self.normalized_xyz_range}"
+        self._align_corners = mpi_align_corners
+        self.compute_mpi_spatial_volume()
+        self.cam, self.render_h, self.render_w = None, None, None
+
+    # mpi_renderer.py:80-103
+    def set_cam(self, fov_deg, render_h, render_w, cam_ray_from_pix_center=True):
+        assert render_h == render_w, f"{render_h}, {render_w}"
+        focal = focal_from_fov(fov_deg, render_w)
+        logger.info(f"camera's FOV: {fov_deg}; focal length: {focal}; size h {render_h}, w {render_w}")
+        self.cam = PinholeCamera(render_h, render_w, focal, cam_ray_from_pix_center)
+        self.render_h, self.render_w = render_h, render_w
+
+    # mpi_renderer.py:105-152
+    def compute_mpi_spatial_volume(self):
+        table = plane_dhw_table(
+            n_planes=self.n_mpi_planes, plane_min_d=self.plane_min_d, plane_max_d=self.plane_max_d,
+            enlarge_factor=self.plan_spatial_enlarge_factor, distance_method=self.plane_distances_sample_method,
+            fov_deg=self.cam_fov, sphere_center=self.sphere_center, sphere_r=self.sphere_r, h_mean=self.horizontal_mean,
+            h_std=self.horizontal_std, v_mean=self.vertical_mean, v_std=self.vertical_std,
+            n_truncated_stds=self.cam_pose_n_truncated_stds, confined=self.use_confined_volume)
+        self.static_mpi_plane_dhws = torch.from_numpy(table)
+        self.dynamic_mpi_plane_dhws = self.static_mpi_plane_dhws
+        self._dhw_dev = None
+
+    # mpi_renderer.py:337-385 (batched)
+    def sample_cam_poses(self, batch_size, horizontal_mean, horizontal_std, vertical_mean, vertical_std, random_pose,
+                         given_yaws=None, given_pitches=None):
+        if given_yaws is None:
+            assert given_pitches is None
+            yaws, pitches = sample_yaw_pitch(batch_size, horizontal_mean, horizontal_std, vertical_mean, vertical_std,
+                                             self.cam_pose_n_truncated_stds, self.cam_sample_method, random_pose)
+        else:
+            yaws, pitches = given_yaws, given_pitches
+        c2w = sphere_poses(yaws.cpu(), pitches.cpu(), self.sphere_center, self.sphere_r).to(self.device)
+        ray_dir, eye, z_dir = self.cam.generate_rays(c2w)
+        # per-view lists of [1,...] tensors, the reference's return convention
+        return (yaws, pitches, c2w, [ray_dir[i:i + 1] for i in range(batch_size)], [eye[i:i + 1] for i in range(batch_size)],
+                [z_dir[i:i + 1] for i in range(batch_size)])
+
+    # mpi_renderer.py:387-469
+    def render(self, batch_mpi_rgbas, render_h, render_w, horizontal_mean=None, horizontal_std=None, vertical_mean=None,
+               vertical_std=None, random_pose=True, given_yaws=None, given_pitches=None, given_cam_infos=None,
+               assert_not_out_of_last_plane=True):
+        horizontal_mean = self.horizontal_mean if horizontal_mean is None else horizontal_mean
+        horizontal_std = self.horizontal_std if horizontal_std is None else horizontal_std
+        vertical_mean = self.vertical_mean if vertical_mean is None else vertical_mean
+        vertical_std = self.vertical_std if vertical_std is None else vertical_std
+        batch_size = batch_mpi_rgbas.shape[0]
+        if render_h != self.render_h or render_w != self.render_w:
+            self.set_cam(self.cam_fov, render_h, render_w)
+        if given_cam_infos is None:
+            yaws, pitches, c2w, rays, eyes, zs = self.sample_cam_poses(batch_size, horizontal_mean, horizontal_std,
+                                                                        vertical_mean, vertical_std, random_pose=random_pose,
+                                                                        given_yaws=given_yaws, given_pitches=given_pitches)
+        else:
+            yaws, pitches, c2w = given_cam_infos["batch_yaws"], given_cam_infos["batch_pitches"], given_cam_infos["batch_tf_c2w"]
+            rays, eyes, zs = given_cam_infos["batch_ray_dir"], given_cam_infos["batch_eye_pos"], given_cam_infos["batch_z_dir"]
+        if not batch_mpi_rgbas.is_cuda:
+            raise RuntimeError("ml_gmpi_b200.MPIRenderer renders on CUDA devices only (no CPU fallback)")
+        dev = batch_mpi_rgbas.device
+        if self._dhw_dev is None or self._dhw_dev.device != dev:
+            self._dhw_dev = self.dynamic_mpi_plane_dhws.to(dev)
+        dhw = self._dhw_dev.reshape(1, -1, 3).expand(batch_size, -1, -1).contiguous()
+        rgba = batch_mpi_rgbas.float()                                          # mpi_renderer.py:446
+        self.mpi.check_shapes(batch_rgba=rgba, batch_dhw=dhw, batch_ray_dir=rays, batch_eye_pos=eyes, batch_z_dir=zs,
+                              separate_background=None)
+        view2mpi, ray_dir, eye, z_dir = MPI.pack_views(rays, eyes, zs, dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.validate == "full":
+            check_range(rgba.detach().contiguous(), flags)                      # mpi_renderer.py:447-449 + mpi.py:185-187
+        img, depth = render_views(rgba, dhw, view2mpi, ray_dir.to(dev), eye.to(dev), z_dir.to(dev),
+                                  align_corners=self._align_corners,
+                                  check_last_plane=bool(assert_not_out_of_last_plane) and self.validate != "off",
+                                  color_minus1_1=True, flags=flags)             # 2c-1 fused, mpi_renderer.py:467
+        self.mpi._flags, self.mpi._flag_ctx = flags, (dhw, eye, c2w, self.sphere_center)
+        if self.validate == "full":
+            f = self.mpi.last_flags()
+            if f & _lib.FLAG_RGBA_RANGE:
+                raise AssertionError(f"{float(rgba.min())}, {float(rgba.max())}")   # message of mpi_renderer.py:449
+            self.mpi.raise_if_flagged()
+        angles = torch.cat([pitches, yaws], -1).to(dev)                         # mpi_renderer.py:464
+        return img, depth, c2w, angles

@@ -1,6 +1,7 @@
 """Host-side camera / pose / plane-geometry code against fixtures produced by
 the unmodified reference (tests/golden/ffhq_dhw.npz, ffhq_cams_20.npz)."""
 import numpy as np
+import pytest
 import torch
 
 from ml_gmpi_b200 import camera, geometry, synth
@@ -53,3 +54,19 @@ def test_synth_case_shapes():
     assert c.rgba.shape == (2, 8, 4, 16, 16) and c.ray_dir.shape == (6, 3, 12, 12)
     assert c.view2mpi.tolist() == [0, 0, 0, 1, 1, 1] and c.dhw.shape == (2, 8, 3)
     assert float(c.rgba.min()) >= 0 and float(c.rgba.max()) <= 1
+
+
+def test_renderer_facade_constructor_matches_reference_table():
+    from ml_gmpi_b200.renderer import MPIRenderer
+    from ml_gmpi_b200.geometry import FFHQ
+    r = MPIRenderer(n_mpi_planes=8, plane_min_d=0.95, plane_max_d=1.12, plan_spatial_enlarge_factor=1.001,
+                    plane_distances_sample_method="inverse", cam_fov=12.6, sphere_center_z=1.0, sphere_r=1.0,
+                    horizontal_mean=0.0, horizontal_std=0.289, vertical_mean=0.0, vertical_std=0.127,
+                    cam_pose_n_truncated_stds=2, cam_sample_method="truncated_gaussian", use_confined_volume=True)
+    np.testing.assert_allclose(r.static_mpi_plane_dhws.numpy(), load_golden("ffhq_dhw")["n8"], rtol=2e-6)
+    r.set_cam(12.6, 20, 20)
+    ref = load_golden("ffhq_cams_20")
+    infos = r.sample_cam_poses(6, 0, 0, 0, 0, True, torch.from_numpy(ref["yaws"]).view(-1, 1), torch.from_numpy(ref["pitches"]).view(-1, 1))
+    np.testing.assert_allclose(torch.cat(infos[3]).numpy(), ref["ray_dir"], atol=3e-7)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        r.render(torch.rand(1, 8, 4, 16, 16), 20, 20)

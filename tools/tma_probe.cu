@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(const __grid_constant__ C
         if (lane == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int tx = (t % p.n_tiles_x) * p.tile_w - 3, ty = (t / p.n_tiles_x) * p.tile_h - 2;
+                const int tx = (t % p.n_tiles_x) * p.tile_w - 4, ty = (t / p.n_tiles_x) * p.tile_h - 2;
                 for (int pl = 0; pl < p.n_planes; ++pl, ++it) {
                     const int s = it % kStages, ph = (it / kStages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
