@@ -17,7 +17,11 @@ namespace gmpi {
 #ifndef GMPI_CONS_WARPS
 #define GMPI_CONS_WARPS 15   // 15 consumer warps + producer = 16 warps = 4 per scheduler, 128 registers per thread
 #endif
-constexpr int kTileW = 64, kTileH = 2 * GMPI_CONS_WARPS;
+#ifndef GMPI_PAIRS
+#define GMPI_PAIRS 2         // packed pixel pairs per thread (each pair = x and x+32 of one tile row)
+#endif
+constexpr int kPairs = GMPI_PAIRS, kPix = 2 * GMPI_PAIRS;
+constexpr int kTileW = 64, kTileH = kPairs * GMPI_CONS_WARPS;
 constexpr int kConsWarps = GMPI_CONS_WARPS, kConsThreads = kConsWarps * 32, kStagedThreads = kConsThreads + 32;
 constexpr int kStages = 3;
 constexpr int kRowsPerOp = 4;
@@ -65,6 +69,17 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
     return bits_f2(r);
 }
+// floor() without the XU pipe: t = x + 1.5*2^23 rounded toward -inf has floor(x) in its mantissa (exact for |x| < 2^22):
+// floor as float = t - 1.5*2^23, floor as int = bits(t) - 0x4b400000.  Anything out of range (huge, inf, NaN) yields an
+// integer far outside any staged box, so the unsigned box test rejects it.
+__device__ __forceinline__ f2 add2_rm(f2 a, f2 b) {
+    unsigned long long r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+constexpr float kFloorMagic = 12582912.0f;        // 1.5 * 2^23
+constexpr int kFloorMagicBits = 0x4b400000;
+
 // a / b correctly rounded with y = RN(1/b), nb = -b (div_by_rcp, two pixels at once)
 __device__ __forceinline__ f2 div2_by_rcp(f2 a, f2 nb, f2 y) {
     const f2 q0 = mul2(a, y);
@@ -74,11 +89,11 @@ __device__ __forceinline__ f2 div2_by_rcp(f2 a, f2 nb, f2 y) {
 
 // A thread's four pixels as two pairs: pair P = (x = lane, x = lane + 32) on tile row 2*warp + P.
 struct RayPairs {
-    f2 rx2[2], ry2[2];   // 2*ray_x, 2*ray_y
-    f2 nrz[2], yrz[2];   // -ray_z, RN(1/ray_z)
+    f2 rx2[kPairs], ry2[kPairs];   // 2*ray_x, 2*ray_y
+    f2 nrz[kPairs], yrz[kPairs];   // -ray_z, RN(1/ray_z)
 };
 struct CoordPairs {
-    f2 ix[2], iy[2], sc[2];
+    f2 ix[kPairs], iy[kPairs], sc[kPairs];
 };
 
 // Texel coordinates on one plane, exact-division fast form; op order of plane_coord (mpi.py:74-90 + unnormalize).
@@ -88,7 +103,7 @@ __device__ __forceinline__ void coords_pairs(const PlaneConst& pc, const RayPair
     const f2 zd = splat(pc.z_diff), ypw = splat(pc.ypw), yph = splat(pc.yph), npw = splat(-pc.pw), nph = splat(-pc.ph);
     const f2 one = splat(1.0f);
 #pragma unroll
-    for (int P = 0; P < 2; ++P) {
+    for (int P = 0; P < kPairs; ++P) {
         const f2 sq = div2_by_rcp(zd, rp.nrz[P], rp.yrz[P]);                 // scale = z_diff / ray_z
         // 2*(e_x + ray_x*scale): mul, THEN add (two roundings, mpi.py:79).  Scalar on purpose: ptxas fuses
         // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS even with --fmad=false), which is not the reference's
@@ -117,17 +132,21 @@ __device__ __forceinline__ void coords_pairs(const PlaneConst& pc, const RayPair
 // if any of the four footprints is not inside the box.
 template <int BW>
 __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float fbx0, float fby0, int rows2, const CoordPairs& c,
-                                             f2 (&T)[2], f2 (&cr)[2], f2 (&cg)[2], f2 (&cb)[2], f2 (&cws)[2]) {
+                                             f2 (&T)[kPairs], f2 (&cr)[kPairs], f2 (&cg)[kPairs], f2 (&cb)[kPairs], f2 (&cws)[kPairs]) {
     const f2 m1 = splat(-1.0f), one = splat(1.0f), nbx = splat(-fbx0), nby = splat(-fby0);
-    f2 fx0[2], fy0[2];
-    int ia[2], ib[2];
+    f2 fx0[kPairs], fy0[kPairs];
+    int ia[kPairs], ib[kPairs];
     bool inbox = true;
+    const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
+    const int cx = kFloorMagicBits + (int)fbx0, cy = kFloorMagicBits + (int)fby0;   // box origins are small integers
+    (void)nbx; (void)nby;
 #pragma unroll
-    for (int P = 0; P < 2; ++P) {
-        fx0[P] = make_float2(floorf(c.ix[P].x), floorf(c.ix[P].y));
-        fy0[P] = make_float2(floorf(c.iy[P].x), floorf(c.iy[P].y));
-        const f2 rx = add2(fx0[P], nbx), ry = add2(fy0[P], nby);     // exact (integers); saturate and fail the test when far away
-        const int rxa = (int)rx.x, rxb = (int)rx.y, rya = (int)ry.x, ryb = (int)ry.y;
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 tx = add2_rm(c.ix[P], magic), ty = add2_rm(c.iy[P], magic);         // floor without the XU pipe
+        fx0[P] = add2(tx, nmagic);                                    // floor as float (exact)
+        fy0[P] = add2(ty, nmagic);
+        const int rxa = __float_as_int(tx.x) - cx, rxb = __float_as_int(tx.y) - cx;   // floor - box origin, as integers
+        const int rya = __float_as_int(ty.x) - cy, ryb = __float_as_int(ty.y) - cy;
         inbox = inbox && (unsigned)rxa <= (unsigned)(BW - 2) && (unsigned)rxb <= (unsigned)(BW - 2) &&
                 (unsigned)rya <= (unsigned)rows2 && (unsigned)ryb <= (unsigned)rows2;
         ia[P] = rya * (4 * BW) + rxa;                                 // [row][channel][x], compile-time pitch
@@ -135,7 +154,7 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float
     }
     if (!inbox) return false;
 #pragma unroll
-    for (int P = 0; P < 2; ++P) {
+    for (int P = 0; P < kPairs; ++P) {
         const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);   // fractional parts (exact)
         const f2 wy0 = fma2(wy1, m1, one);
         const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
@@ -145,7 +164,11 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float
     fma2(make_float2(ta[(4 + ch) * BW + 1], tb[(4 + ch) * BW + 1]), w11,                                       \
          fma2(make_float2(ta[(4 + ch) * BW], tb[(4 + ch) * BW]), w10,                                          \
               fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
+#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 1
+        const f2 r = GMPI_TAP(0), g = r, b = r, a = GMPI_TAP(3);   // knock-out experiment: half the LDS
+#else
         const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2), a = GMPI_TAP(3);
+#endif
 #undef GMPI_TAP
         const f2 w = mul2(a, T[P]);                     // mpi.py:423
         cr[P] = fma2(w, r, cr[P]);                      // mpi.py:430
@@ -153,6 +176,54 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float
         cb[P] = fma2(w, b, cb[P]);
         cws[P] = fma2(w, c.sc[P], cws[P]);              // depth_i = scale * (ray . z_dir), mpi.py:150
         T[P] = fma2(w, m1, T[P]);   // T(1-a); the reference's +1e-10 changes any later weight by < 1e-10 absolute
+    }
+    return true;
+}
+
+// Same with a run-time box width (one code body for every width; eight address adds per pixel instead of immediates).
+__device__ __forceinline__ bool sample_pairs_dyn(const float* __restrict__ sb, int bw, float fbx0, float fby0, int rows2, const CoordPairs& c,
+                                                 f2 (&T)[kPairs], f2 (&cr)[kPairs], f2 (&cg)[kPairs], f2 (&cb)[kPairs], f2 (&cws)[kPairs]) {
+    const f2 m1 = splat(-1.0f), one = splat(1.0f), nbx = splat(-fbx0), nby = splat(-fby0);
+    f2 fx0[kPairs], fy0[kPairs];
+    int ia[kPairs], ib[kPairs];
+    bool inbox = true;
+    const int bw4 = 4 * bw;
+    const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
+    const int cx = kFloorMagicBits + (int)fbx0, cy = kFloorMagicBits + (int)fby0;   // box origins are small integers
+    (void)nbx; (void)nby;
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 tx = add2_rm(c.ix[P], magic), ty = add2_rm(c.iy[P], magic);
+        fx0[P] = add2(tx, nmagic);                                    // floor as float (exact)
+        fy0[P] = add2(ty, nmagic);
+        const int rxa = __float_as_int(tx.x) - cx, rxb = __float_as_int(tx.y) - cx;   // floor - box origin, as integers
+        const int rya = __float_as_int(ty.x) - cy, ryb = __float_as_int(ty.y) - cy;
+        inbox = inbox && (unsigned)rxa <= (unsigned)(bw - 2) && (unsigned)rxb <= (unsigned)(bw - 2) &&
+                (unsigned)rya <= (unsigned)rows2 && (unsigned)ryb <= (unsigned)rows2;
+        ia[P] = rya * bw4 + rxa;
+        ib[P] = ryb * bw4 + rxb;
+    }
+    if (!inbox) return false;
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);
+        const f2 wy0 = fma2(wy1, m1, one);
+        const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
+        const float* ta = sb + ia[P];
+        const float* tb = sb + ib[P];
+        f2 v[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float* a0 = ta + ch * bw; const float* b0 = tb + ch * bw;
+            v[ch] = fma2(make_float2(a0[bw4 + 1], b0[bw4 + 1]), w11,
+                         fma2(make_float2(a0[bw4], b0[bw4]), w10, fma2(make_float2(a0[1], b0[1]), w01, mul2(make_float2(a0[0], b0[0]), w00))));
+        }
+        const f2 w = mul2(v[3], T[P]);
+        cr[P] = fma2(w, v[0], cr[P]);
+        cg[P] = fma2(w, v[1], cg[P]);
+        cb[P] = fma2(w, v[2], cb[P]);
+        cws[P] = fma2(w, c.sc[P], cws[P]);
+        T[P] = fma2(w, m1, T[P]);
     }
     return true;
 }
@@ -238,11 +309,19 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     mt.rows2 = rows - 2;
                     mt.bw_mode = bw | (mode << 16);
                     s_meta[s] = mt;
+#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
+                    mbar_arrive(&s_full[s]);                      // knock-out experiment: no TMA traffic at all
+#else
                     if (n_ops > 0) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16));
                     else mbar_arrive(&s_full[s]);
+#endif
                 }
                 __syncwarp();
+#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
+                if (false) {
+#else
                 if (lane < n_ops) {
+#endif
                     float* dst = s_buf + (size_t)s * kStageFloats + (size_t)lane * kRowsPerOp * 4 * bw;
                     tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
                 }
@@ -250,7 +329,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
         }
     } else {
         // ================================ consumer warps ================================
-        // warp w owns rows 2w, 2w+1 of the tile; a lane owns x = lane and lane+32 on both rows
+        // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them
         const bool check_last = (p.options & GMPI_CHECK_LAST_PLANE) != 0;
         const bool minus1_1 = (p.options & GMPI_COLOR_MINUS1_1) != 0;
         uint32_t it = 0;
@@ -276,18 +355,18 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 v_table = v;
             }
             const float* rays = p.ray_dir + (size_t)v * 3 * img;
-            RayConst rc[4];      // scalar copies, only for the generic (rare) body and the epilogue
+            RayConst rc[kPix];   // scalar copies, only for the generic (rare) body and the epilogue
             RayPairs rp;
             bool rays_fast = (in_safe_range(ev[0]) || ev[0] == 0.0f) && (in_safe_range(ev[1]) || ev[1] == 0.0f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int px = min(px0 + lane + 32 * (q & 1), p.W - 1), py = min(py0 + 2 * warp + (q >> 1), p.H - 1);
+            for (int q = 0; q < kPix; ++q) {
+                const int px = min(px0 + lane + 32 * (q & 1), p.W - 1), py = min(py0 + kPairs * warp + (q >> 1), p.H - 1);
                 const float* rd = rays + (size_t)py * p.W + px;
                 rc[q] = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
                 rays_fast = rays_fast && rc[q].fast && fabsf(rc[q].rx2) <= 0x1p40f && fabsf(rc[q].ry2) <= 0x1p40f;
             }
 #pragma unroll
-            for (int P = 0; P < 2; ++P) {
+            for (int P = 0; P < kPairs; ++P) {
                 rp.rx2[P] = make_float2(rc[2 * P].rx2, rc[2 * P + 1].rx2);
                 rp.ry2[P] = make_float2(rc[2 * P].ry2, rc[2 * P + 1].ry2);
                 rp.nrz[P] = make_float2(-rc[2 * P].rz, -rc[2 * P + 1].rz);
@@ -297,26 +376,42 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             // warp-uniform: every ray of this warp is in the range where the reciprocal+FMA division is exact and no
             // coordinate can be NaN, so the per-plane body needs no per-pixel range checks
             const bool warp_fast = __all_sync(0xffffffffu, rays_fast);
-            f2 T[2] = {splat(1.f), splat(1.f)}, cr[2] = {splat(0.f), splat(0.f)}, cg[2] = {splat(0.f), splat(0.f)},
-               cb[2] = {splat(0.f), splat(0.f)}, cws[2] = {splat(0.f), splat(0.f)};
+            f2 T[kPairs], cr[kPairs], cg[kPairs], cb[kPairs], cws[kPairs];
+#pragma unroll
+            for (int P = 0; P < kPairs; ++P) { T[P] = splat(1.f); cr[P] = cg[P] = cb[P] = cws[P] = splat(0.f); }
             const float* plane = p.rgba + (size_t)m * N * 4 * tex;
             // software pipeline: the coordinates of plane i+1 are computed while plane i's taps are in flight
+#ifndef GMPI_SWPIPE
+#define GMPI_SWPIPE 0   // measured: computing plane i+1 coordinates early costs registers and loses ~3%
+#endif
             CoordPairs cn;
             PlaneConst pcn = s_pc[0];
             bool fast_n = warp_fast && pcn.fast != 0.0f;
+#if GMPI_SWPIPE
             if (fast_n) coords_pairs<kAlignCorners>(pcn, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cn);
+#endif
             for (int i = 0; i < N; ++i, ++it, plane += 4 * tex) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
+#if GMPI_SWPIPE
                 const CoordPairs cc = cn;
                 const PlaneConst pcc = pcn;
                 const bool fast_c = fast_n;
+#else
+                const PlaneConst pcc = s_pc[i];
+                const bool fast_c = warp_fast && pcc.fast != 0.0f;
+                CoordPairs cc;
+                if (fast_c) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
+#endif
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloats;
                 const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
                 bool done = false;
                 if (fast_c && mode == 0) {
+#if defined(GMPI_DYN_PITCH) && GMPI_DYN_PITCH
+                    done = sample_pairs_dyn(sb, bw, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws);
+#else
                     switch (bw) {   // warp-uniform
                         case 56: done = sample_pairs<56>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                         case 64: done = sample_pairs<64>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
@@ -324,11 +419,14 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                         case 80: done = sample_pairs<80>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                         default: done = sample_pairs<88>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                     }
+#endif
                 }
+#if GMPI_SWPIPE
                 // next plane's constants and coordinates (independent of the staged data)
                 pcn = s_pc[min(i + 1, N - 1)];
                 fast_n = warp_fast && pcn.fast != 0.0f;
                 if (fast_n) coords_pairs<kAlignCorners>(pcn, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cn);
+#endif
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----
                     const int bw4 = 4 * bw;
@@ -339,7 +437,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     float* cbs = reinterpret_cast<float*>(cb);
                     float* cwss = reinterpret_cast<float*>(cws);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < kPix; ++q) {
                         const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);
                         const float rxx = fx - mt.fbx0, ryy = fy - mt.fby0;
@@ -372,15 +470,15 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 if (lane == 0) mbar_arrive(&s_empty[s]);
                 if (check_last && i == N - 1) {     // assert_not_out_of_last_plane, mpi.py:103-109 (once per tile)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < kPix; ++q) {
                         const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
                         if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
                     }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int px = px0 + lane + 32 * (q & 1), py = py0 + 2 * warp + (q >> 1);
+            for (int q = 0; q < kPix; ++q) {
+                const int px = px0 + lane + 32 * (q & 1), py = py0 + kPairs * warp + (q >> 1);
                 if (px >= p.W || py >= p.H) continue;
                 const size_t pix = (size_t)py * p.W + px;
                 float o0 = (q & 1) ? cr[q >> 1].y : cr[q >> 1].x, o1 = (q & 1) ? cg[q >> 1].y : cg[q >> 1].x;
