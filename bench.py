@@ -187,8 +187,18 @@ def main():
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
     color = torch.empty((B, 3, R, R), device=dev)
     depth = torch.empty((B, 1, R, R), device=dev)
-    frames_all = torch.empty((world * B, 4, R, R), device=dev) if world > 1 else None
-    frames_local = torch.empty((B, 4, R, R), device=dev) if world > 1 else None
+    frames_all = frames_local = fused = None
+    gather_mode = "none"
+    if world > 1:
+        try:    # all-gather fused into the render epilogue: peer stores into symmetric memory over NVLink
+            fused = gdist.FrameGather(B, R, R, dev)
+            gather_mode = "fused: render epilogue stores frames into every rank's symmetric-memory buffer (NVLink), 1 device barrier per step"
+        except Exception as ex:   # no symmetric memory on this box: render, then ncclAllGather
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({type(ex).__name__}: {ex}); using ncclAllGather", file=sys.stderr)
+            frames_all = torch.empty((world * B, 4, R, R), device=dev)
+            frames_local = torch.empty((B, 4, R, R), device=dev)
+            gather_mode = "render, then one ncclAllGather of [V,4,H,W] frames"
     stream = torch.cuda.current_stream(dev)
     opts = _lib.OPT_ALIGN_CORNERS | _lib.OPT_CHECK_LAST_PLANE | _lib.OPT_COLOR_MINUS1_1
     launches = [0]
@@ -200,11 +210,20 @@ def main():
                                            stream.cuda_stream))
         launches[0] += 1
 
+    def render_gather():
+        fused.render(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, flags, check_last_plane=True,
+                     color_minus1_1=True)
+        launches[0] += 1
+
     def step():
-        render()
-        if world > 1:   # the one collective of the path: all-gather of the rendered frames
-            frames_local[:, :3].copy_(color); frames_local[:, 3:].copy_(depth)
-            dist.all_gather_into_tensor(frames_all, frames_local)
+        if fused is not None:   # the one collective of the path, fused into the kernel
+            render_gather()
+            fused.finish()
+        else:
+            render()
+            if world > 1:
+                frames_local[:, :3].copy_(color); frames_local[:, 3:].copy_(depth)
+                dist.all_gather_into_tensor(frames_all, frames_local)
 
     def barrier():
         if world > 1:
@@ -228,11 +247,16 @@ def main():
     ev[0].record(stream)
     for i in range(args.steps):
         kev[i][0].record(stream)
-        render()
-        kev[i][1].record(stream)
-        if world > 1:
-            frames_local[:, :3].copy_(color); frames_local[:, 3:].copy_(depth)
-            dist.all_gather_into_tensor(frames_all, frames_local)
+        if fused is not None:
+            render_gather()
+            kev[i][1].record(stream)
+            fused.finish()
+        else:
+            render()
+            kev[i][1].record(stream)
+            if world > 1:
+                frames_local[:, :3].copy_(color); frames_local[:, 3:].copy_(depth)
+                dist.all_gather_into_tensor(frames_all, frames_local)
     ev[1].record(stream)
     barrier()
     t_wall1 = time.time()
@@ -334,7 +358,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if (NP, R, B) == (N_PLANES, RES, BATCH) else f"{NP} planes, {R}^2, {B} MPIs x 1 view per GPU",
-                       "planes": NP, "tex": R, "img": R, "mpis_per_gpu": B, "views_per_gpu": B, "parallelism": f"views sharded x{world}, 1 all-gather of frames",
+                       "planes": NP, "tex": R, "img": R, "mpis_per_gpu": B, "views_per_gpu": B, "parallelism": f"views sharded x{world}; all-gather of frames: {gather_mode}",
                        "l2": f"inputs {case.rgba.numel() * 4 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "validate": "geometric flags fused in-kernel; range scan off in the timed region"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roofline, "cpu_baseline": cpu, "train_step": train,

@@ -77,6 +77,20 @@ int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float*
                         uint32_t options, void* stream);
 
 /*
+ * Forward with the all-gather of frames fused into the epilogue (multi-GPU).  Instead of
+ * color/depth, every finished pixel of view v is stored as a packed frame [4,H,W] = (R,G,B,depth) at frame index
+ * frame_offset + v of EVERY buffer in peer_frames: a DEVICE array of n_peers base pointers to [F,4,H,W] fp32 buffers,
+ * one per rank, peer-mapped over NVLink (e.g. torch symmetric memory, cudaIpc).  The stores are posted writes that overlap
+ * the remaining compute; the caller makes them visible with a barrier across ranks after the kernel.  Replaces the
+ * render + ncclAllGather pair; the reference has no counterpart (its renderer is single-GPU, gloo barriers only).
+ */
+int gmpi_mpi_render_fwd_gather(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                               const float* ray_dir, const float* eye, const float* z_dir,
+                               float* const* peer_frames, int n_peers, int frame_offset, uint32_t* flags,
+                               int M, int V, int N, int Ht, int Wt, int H, int W,
+                               uint32_t options, void* stream);
+
+/*
  * Backward: d(sum(color*g_color) + sum(depth*g_depth)) / d rgba, what torch autograd produces for
  * MPI.forward (only the sampled rgba carries gradient: mpi.py:65,148 run under no_grad).
  * g_depth may be NULL.  Views of one MPI accumulate into the same g_rgba slab (the `expand` of

@@ -24,7 +24,26 @@ struct RenderParams {
     float* g_rgba;            // bwd
     int M, V, N, Ht, Wt, H, W;
     uint32_t options;
+    // fused all-gather (optional): frames [*,4,H,W] (RGB + depth) of view v are stored into every peer's buffer at
+    // frame index frame_offset + v instead of color/depth.  peer_frames is a device array of n_peers base pointers.
+    float* const* peer_frames;
+    int n_peers, frame_offset;
 };
+
+// Store one finished pixel: plain outputs, or the same frame slot of every rank's gather buffer (NVLink peer stores).
+__device__ __forceinline__ void store_pixel(const RenderParams& p, int v, size_t img, size_t pix, float c0, float c1, float c2, float dep) {
+    if (p.n_peers > 0) {
+        const size_t fo = (size_t)(p.frame_offset + v) * 4 * img + pix;
+        for (int r = 0; r < p.n_peers; ++r) {
+            float* f = p.peer_frames[r] + fo;
+            f[0] = c0; f[img] = c1; f[2 * img] = c2; f[3 * img] = dep;
+        }
+    } else {
+        float* co = p.color + (size_t)v * 3 * img + pix;
+        co[0] = c0; co[img] = c1; co[2 * img] = c2;
+        p.depth[(size_t)v * img + pix] = dep;
+    }
+}
 
 // Per (view, plane) constants, staged in shared memory once per CTA.
 //   a = {z_diff, pw, ph, fast}   b = {rcp(pw), rcp(ph), -, -}

@@ -487,9 +487,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 if (minus1_1) {
                     o0 = fmaf(2.0f, o0, -1.0f); o1 = fmaf(2.0f, o1, -1.0f); o2 = fmaf(2.0f, o2, -1.0f);
                 }
-                float* co = p.color + (size_t)v * 3 * img + pix;
-                co[0] = o0; co[img] = o1; co[2 * img] = o2;
-                p.depth[(size_t)v * img + pix] = ws * rc[q].dz;
+                store_pixel(p, v, img, pix, o0, o1, o2, ws * rc[q].dz);
             }
         }
         if (flag) atomicOr(p.flags, flag);

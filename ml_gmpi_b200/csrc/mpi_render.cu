@@ -107,11 +107,7 @@ mpi_fwd_direct_kernel(const RenderParams p) {
             cg = fmaf(2.0f, cg, -1.0f);
             cb = fmaf(2.0f, cb, -1.0f);
         }
-        float* co = p.color + (size_t)v * 3 * img + pix;
-        co[0] = cr;
-        co[img] = cg;
-        co[2 * img] = cb;
-        p.depth[(size_t)v * img + pix] = dep;
+        store_pixel(p, v, img, pix, cr, cg, cb, dep);
     }
     if (flag) atomicOr(p.flags, flag);
 }
@@ -358,16 +354,23 @@ const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
     return staged_eligible(1 << 20, N, Ht, Wt, H, W) ? "fwd_staged_tma_64x32" : "fwd_direct_32x8";
 }
 
-int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
-                        const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags, int M,
-                        int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
+static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                           const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags,
+                           float* const* peer_frames, int n_peers, int frame_offset, int M, int V, int N, int Ht, int Wt,
+                           int H, int W, uint32_t options, void* stream) {
     int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
     if (rc) return rc;
-    if (!color || !depth || !flags) return fail(GMPI_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (!flags) return fail(GMPI_ERR_INVALID_ARGUMENT, "null flags pointer");
+    if (n_peers > 0) {
+        if (!peer_frames || frame_offset < 0) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad peer frame buffers");
+    } else if (!color || !depth) {
+        return fail(GMPI_ERR_INVALID_ARGUMENT, "null output pointer");
+    }
     if (V == 0) return GMPI_OK;
     RenderParams p{};
     p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
     p.color = color; p.depth = depth; p.flags = flags;
+    p.peer_frames = peer_frames; p.n_peers = n_peers; p.frame_offset = frame_offset;
     p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
     cudaStream_t st = (cudaStream_t)stream;
     if (staged_eligible(V, N, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)) {
@@ -411,6 +414,22 @@ int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float*
     }
     GMPI_CUDA_OK(cudaGetLastError());
     return GMPI_OK;
+}
+
+int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                        const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags, int M,
+                        int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags, nullptr, 0, 0, M, V, N, Ht, Wt, H, W,
+                           options, stream);
+}
+
+int gmpi_mpi_render_fwd_gather(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                               const float* eye, const float* z_dir, float* const* peer_frames, int n_peers,
+                               int frame_offset, uint32_t* flags, int M, int V, int N, int Ht, int Wt, int H, int W,
+                               uint32_t options, void* stream) {
+    if (n_peers < 1) return fail(GMPI_ERR_INVALID_ARGUMENT, "n_peers must be >= 1");
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, nullptr, nullptr, flags, peer_frames, n_peers, frame_offset,
+                           M, V, N, Ht, Wt, H, W, options, stream);
 }
 
 int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,

@@ -50,3 +50,44 @@ def all_gather_frames(frames: torch.Tensor, counts: List[int] = None, group=None
     out = torch.empty((world * vmax,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=frames.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * vmax: r * vmax + counts[r]] for r in range(world)], dim=0)
+
+
+class FrameGather:
+    """All-gather of rendered frames fused into the render kernel (the one collective of the path).
+
+    Every rank owns a symmetric-memory buffer [world * frames_per_rank, 4, H, W] that all peers map over NVLink
+    (torch.distributed._symmetric_memory).  `render()` launches the forward kernel with the peers' buffer pointers: the
+    epilogue stores each finished pixel into frame slot rank * frames_per_rank + v of EVERY rank's buffer, so the gather
+    overlaps the render tile by tile (posted NVLink writes) instead of following it as a separate ncclAllGather;
+    `finish()` is the device-side barrier that makes the remote stores visible.  `frames` is then the gathered tensor.
+    """
+
+    def __init__(self, frames_per_rank: int, H: int, W: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.frames_per_rank, self.H, self.W = frames_per_rank, H, W
+        self.frames = symm_mem.empty((self.world * frames_per_rank, 4, H, W), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.frames, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(ptrs) == self.world
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)   # device array of float* (one per rank)
+
+    def render(self, rgba, dhw, view2mpi, ray_dir, eye, z_dir, flags, *, align_corners=True, check_last_plane=False,
+               color_minus1_1=False):
+        from . import _lib
+        lib = _lib.load()
+        M, N, _, Ht, Wt = rgba.shape
+        V = ray_dir.shape[0]
+        assert V <= self.frames_per_rank and ray_dir.shape[2:] == (self.H, self.W)
+        options = (_lib.OPT_ALIGN_CORNERS if align_corners else 0) | (_lib.OPT_CHECK_LAST_PLANE if check_last_plane else 0) \
+            | (_lib.OPT_COLOR_MINUS1_1 if color_minus1_1 else 0)
+        with torch.cuda.device(rgba.device):
+            _lib.check(lib.gmpi_mpi_render_fwd_gather(
+                rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
+                self.peer_ptrs.data_ptr(), self.world, self.rank * self.frames_per_rank, flags.data_ptr(),
+                M, V, N, Ht, Wt, self.H, self.W, options, torch.cuda.current_stream(rgba.device).cuda_stream))
+
+    def finish(self):
+        """Barrier across ranks on the current stream: after it, every rank's `frames` holds all ranks' frames."""
+        self.handle.barrier(channel=0)
