@@ -104,6 +104,23 @@ int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float*
                         uint32_t options, void* stream);
 
 /*
+ * Training pair.  gmpi_mpi_render_fwd_train = gmpi_mpi_render_fwd that additionally saves the transmittance in front of
+ * every plane, transmittance [V,N,H,W] (T_i = prod_{j<i}(1 - alpha_j), mpi.py:421-423) -- what torch autograd keeps alive as
+ * `weights`/`cumprod` tensors, here 4 bytes per (pixel, plane).  gmpi_mpi_render_bwd_saved consumes it: one staged
+ * back-to-front sweep instead of the two-pass kernel (falls back to gmpi_mpi_render_bwd for shapes the staged path skips).
+ */
+int gmpi_mpi_render_fwd_train(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                              const float* ray_dir, const float* eye, const float* z_dir,
+                              float* color, float* depth, float* transmittance, uint32_t* flags,
+                              int M, int V, int N, int Ht, int Wt, int H, int W,
+                              uint32_t options, void* stream);
+int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                              const float* ray_dir, const float* eye, const float* z_dir,
+                              const float* transmittance, const float* g_color, const float* g_depth,
+                              float* g_rgba, int M, int V, int N, int Ht, int Wt, int H, int W,
+                              uint32_t options, void* stream);
+
+/*
  * Range checks of MPIRenderer.render (mpi_renderer.py:447-449) and MPI.check_shapes
  * (mpi.py:185-187) in one streaming pass: sets GMPI_FLAG_RGBA_RANGE / GMPI_FLAG_ALPHA_RANGE.
  */

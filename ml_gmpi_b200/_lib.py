@@ -21,7 +21,7 @@ ABI_VERSION = 1
 
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
-    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_bwd", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed",
+    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed",
 ]
 
 _lib = None
@@ -52,6 +52,10 @@ def load():
     lib.gmpi_mpi_render_fwd.argtypes = [vp] * 9 + [i] * 7 + [u32, vp]
     lib.gmpi_mpi_render_fwd_gather.restype = i
     lib.gmpi_mpi_render_fwd_gather.argtypes = [vp] * 7 + [i, i, vp] + [i] * 7 + [u32, vp]
+    lib.gmpi_mpi_render_fwd_train.restype = i
+    lib.gmpi_mpi_render_fwd_train.argtypes = [vp] * 10 + [i] * 7 + [u32, vp]
+    lib.gmpi_mpi_render_bwd_saved.restype = i
+    lib.gmpi_mpi_render_bwd_saved.argtypes = [vp] * 10 + [i] * 7 + [u32, vp]
     lib.gmpi_mpi_render_bwd.restype = i
     lib.gmpi_mpi_render_bwd.argtypes = [vp] * 9 + [i] * 7 + [u32, vp]
     lib.gmpi_mpi_check_range.restype = i

@@ -1,0 +1,225 @@
+// Backward, TMA-staged persistent variant: d(sum(color*g_color) + sum(depth*g_depth)) / d rgba.
+//
+// Same tile / ring / producer machinery as the forward (mpi_fwd_staged.cuh), planes walked BACK TO FRONT.  The forward,
+// run in training mode, saved the transmittance T_i in front of every plane ([V,N,H,W]); with it one sweep suffices:
+//     q_i = G.rgb_i + G_d*depth_i          d_i = q_i - R_i            (R_{N-1} = 0)
+//     dL/d rgb_i = G * a_i * T_i           dL/d a_i = T_i * d_i       R_{i-1} = R_i + a_i * d_i
+// which is autograd's  T_i q_i - (sum_{k>i} a_k q_k P_k) / (1 - a_i + 1e-10)  (cumprod_backward) without the division
+// (1e-10 when a_i == 1) and without cancellation.  The four channels are sampled from the staged box (packed f32x2 math,
+// as in the forward) and every value is scattered through the four bilinear weights with red.global.add.f32
+// (grid_sampler_2d_backward); taps outside the texture are skipped (padding_mode="zeros").
+#pragma once
+#include "mpi_fwd_staged.cuh"
+
+namespace gmpi {
+
+struct GradPairs {
+    f2 g0[kPairs], g1[kPairs], g2[kPairs], gs[kPairs];   // upstream colour gradient and g_depth * (ray . z_dir)
+};
+
+// scatter one pixel's four channel gradients through its bilinear footprint with north-west texel (x0, y0)
+__device__ __forceinline__ void scatter_pixel(float* __restrict__ gplane, size_t tex, int Wt, int Ht, int x0, int y0, float v0, float v1,
+                                              float v2, float v3, float w00, float w01, float w10, float w11) {
+    const bool vx0 = (unsigned)x0 < (unsigned)Wt, vx1 = (unsigned)(x0 + 1) < (unsigned)Wt;
+    const bool vy0 = (unsigned)y0 < (unsigned)Ht, vy1 = (unsigned)(y0 + 1) < (unsigned)Ht;
+    float* b = gplane + ((long long)y0 * Wt + x0);
+    const float vals[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int c = 0; c < 4; ++c, b += tex) {
+        if (vx0 && vy0) atomicAdd(b, vals[c] * w00);
+        if (vx1 && vy0) atomicAdd(b + 1, vals[c] * w01);
+        if (vx0 && vy1) atomicAdd(b + Wt, vals[c] * w10);
+        if (vx1 && vy1) atomicAdd(b + Wt + 1, vals[c] * w11);
+    }
+}
+
+// Fast body: four pixels (two packed pairs) from a staged box of compile-time width BW.  Returns false (nothing done) if
+// any footprint is not inside the box.
+template <int BW>
+__device__ __forceinline__ bool bwd_pairs(const float* __restrict__ sb, float fbx0, float fby0, int rows2, const CoordPairs& c,
+                                          const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], float* __restrict__ gplane,
+                                          size_t tex, int Wt, int Ht) {
+    const f2 m1 = splat(-1.0f), one = splat(1.0f);
+    const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
+    const int bx0 = (int)fbx0, by0 = (int)fby0;
+    const int cx = kFloorMagicBits + bx0, cy = kFloorMagicBits + by0;
+    f2 fx0[kPairs], fy0[kPairs];
+    int rxa[kPairs], rxb[kPairs], rya[kPairs], ryb[kPairs];
+    bool inbox = true;
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 tx = add2_rm(c.ix[P], magic), ty = add2_rm(c.iy[P], magic);
+        fx0[P] = add2(tx, nmagic);
+        fy0[P] = add2(ty, nmagic);
+        rxa[P] = __float_as_int(tx.x) - cx; rxb[P] = __float_as_int(tx.y) - cx;
+        rya[P] = __float_as_int(ty.x) - cy; ryb[P] = __float_as_int(ty.y) - cy;
+        inbox = inbox && (unsigned)rxa[P] <= (unsigned)(BW - 2) && (unsigned)rxb[P] <= (unsigned)(BW - 2) &&
+                (unsigned)rya[P] <= (unsigned)rows2 && (unsigned)ryb[P] <= (unsigned)rows2;
+    }
+    if (!inbox) return false;
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);
+        const f2 wy0 = fma2(wy1, m1, one);
+        const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
+        const float* ta = sb + (rya[P] * (4 * BW) + rxa[P]);
+        const float* tb = sb + (ryb[P] * (4 * BW) + rxb[P]);
+#define GMPI_TAP(ch)                                                                                           \
+    fma2(make_float2(ta[(4 + ch) * BW + 1], tb[(4 + ch) * BW + 1]), w11,                                       \
+         fma2(make_float2(ta[(4 + ch) * BW], tb[(4 + ch) * BW]), w10,                                          \
+              fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
+        const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2), a = GMPI_TAP(3);
+#undef GMPI_TAP
+        const f2 q = fma2(G.g0[P], r, fma2(G.g1[P], g, fma2(G.g2[P], b, mul2(G.gs[P], c.sc[P]))));
+        const f2 d = fma2(R[P], m1, q);                 // q - R
+        const f2 w = mul2(a, T[P]);
+        const f2 ga = mul2(T[P], d);
+        R[P] = fma2(a, d, R[P]);
+        const f2 gr = mul2(G.g0[P], w), gg = mul2(G.g1[P], w), gb = mul2(G.g2[P], w);
+        scatter_pixel(gplane, tex, Wt, Ht, bx0 + rxa[P], by0 + rya[P], gr.x, gg.x, gb.x, ga.x, w00.x, w01.x, w10.x, w11.x);
+        scatter_pixel(gplane, tex, Wt, Ht, bx0 + rxb[P], by0 + ryb[P], gr.y, gg.y, gb.y, ga.y, w00.y, w01.y, w10.y, w11.y);
+    }
+    return true;
+}
+
+template <bool kAlignCorners>
+__global__ void __launch_bounds__(kStagedThreads, 1)
+mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* s_buf = reinterpret_cast<float*>(smem_raw);
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kStageFloats * 4);
+    __shared__ StageMeta s_meta[kStages];
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kConsWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int Ht = p.Ht, Wt = p.Wt, N = p.N;
+    const float fWt = (float)Wt, fHt = (float)Ht;
+    const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    const size_t img = (size_t)p.H * p.W;
+    const int tiles_per_view = tiles_x * tiles_y;
+    const int n_tiles = tiles_per_view * p.V;
+
+    if (warp == kConsWarps) {
+        staged_producer<kAlignCorners, true>(p, maps, s_buf, s_meta, s_full, s_empty, tiles_x, tiles_y, lane);
+    } else {
+        uint32_t it = 0;
+        const size_t tex = (size_t)Ht * Wt;
+        const float gscale = (p.options & GMPI_COLOR_MINUS1_1) ? 2.0f : 1.0f;   // upstream gradient is w.r.t. 2*color-1
+        int v_table = -1;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int v = t / tiles_per_view, tt = t - v * tiles_per_view;
+            const int px0 = (tt % tiles_x) * kTileW, py0 = (tt / tiles_x) * kTileH;
+            const int m = __ldg(p.view2mpi + v);
+            const float* e = p.eye + 3 * v;
+            const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
+            const float zd[3] = {__ldg(p.z_dir + 3 * v), __ldg(p.z_dir + 3 * v + 1), __ldg(p.z_dir + 3 * v + 2)};
+            if (v != v_table) {
+                consumer_bar_sync();
+                for (int i = threadIdx.x; i < N; i += kConsThreads) s_pc[i] = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
+                consumer_bar_sync();
+                v_table = v;
+            }
+            const float* rays = p.ray_dir + (size_t)v * 3 * img;
+            RayConst rc[kPix];
+            RayPairs rp;
+            GradPairs G;
+            size_t pix[kPix];
+            bool valid[kPix];
+            float gq[kPix][4];
+            bool rays_fast = (in_safe_range(ev[0]) || ev[0] == 0.0f) && (in_safe_range(ev[1]) || ev[1] == 0.0f);
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) {
+                const int pxq = px0 + lane + 32 * (q & 1), pyq = py0 + kPairs * warp + (q >> 1);
+                valid[q] = pxq < p.W && pyq < p.H;
+                pix[q] = (size_t)min(pyq, p.H - 1) * p.W + min(pxq, p.W - 1);
+                const float* rd = rays + pix[q];
+                rc[q] = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+                rays_fast = rays_fast && rc[q].fast && fabsf(rc[q].rx2) <= 0x1p40f && fabsf(rc[q].ry2) <= 0x1p40f;
+                // pixels of the tile overhang carry zero upstream gradient: they scatter nothing
+                const float* gc = p.g_color + (size_t)v * 3 * img + pix[q];
+                gq[q][0] = valid[q] ? gscale * __ldg(gc) : 0.0f;
+                gq[q][1] = valid[q] ? gscale * __ldg(gc + img) : 0.0f;
+                gq[q][2] = valid[q] ? gscale * __ldg(gc + 2 * img) : 0.0f;
+                gq[q][3] = (valid[q] && p.g_depth) ? __ldg(p.g_depth + (size_t)v * img + pix[q]) * rc[q].dz : 0.0f;
+            }
+#pragma unroll
+            for (int P = 0; P < kPairs; ++P) {
+                rp.rx2[P] = make_float2(rc[2 * P].rx2, rc[2 * P + 1].rx2);
+                rp.ry2[P] = make_float2(rc[2 * P].ry2, rc[2 * P + 1].ry2);
+                rp.nrz[P] = make_float2(-rc[2 * P].rz, -rc[2 * P + 1].rz);
+                rp.yrz[P] = make_float2(rc[2 * P].yrz, rc[2 * P + 1].yrz);
+                G.g0[P] = make_float2(gq[2 * P][0], gq[2 * P + 1][0]);
+                G.g1[P] = make_float2(gq[2 * P][1], gq[2 * P + 1][1]);
+                G.g2[P] = make_float2(gq[2 * P][2], gq[2 * P + 1][2]);
+                G.gs[P] = make_float2(gq[2 * P][3], gq[2 * P + 1][3]);
+            }
+            const f2 ex2 = splat(rc[0].ex2), ey2 = splat(rc[0].ey2), hsx2 = splat(hsx), hsy2 = splat(hsy);
+            const bool warp_fast = __all_sync(0xffffffffu, rays_fast);
+            f2 R[kPairs];
+#pragma unroll
+            for (int P = 0; P < kPairs; ++P) R[P] = splat(0.0f);
+            const float* tsv = p.transmittance + (size_t)v * N * img;
+            for (int ii = 0; ii < N; ++ii, ++it) {
+                const int i = N - 1 - ii;
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                f2 T[kPairs];
+#pragma unroll
+                for (int P = 0; P < kPairs; ++P)      // saved by the forward; issued before the wait to hide the latency
+                    T[P] = make_float2(__ldg(tsv + (size_t)i * img + pix[2 * P]), __ldg(tsv + (size_t)i * img + pix[2 * P + 1]));
+                const PlaneConst pcc = s_pc[i];
+                const bool fast_c = warp_fast && pcc.fast != 0.0f;
+                CoordPairs cc;
+                if (fast_c) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
+                float* gplane = p.g_rgba + ((size_t)m * N + i) * 4 * tex;
+                mbar_wait(&s_full[s], ph);
+                const StageMeta mt = s_meta[s];
+                const float* sb = s_buf + s * kStageFloats;
+                const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
+                bool done = false;
+                if (fast_c && mode == 0) {
+                    switch (bw) {   // warp-uniform
+                        case 56: done = bwd_pairs<56>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
+                        case 64: done = bwd_pairs<64>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
+                        case 72: done = bwd_pairs<72>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
+                        case 80: done = bwd_pairs<80>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
+                        default: done = bwd_pairs<88>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[s]);     // the generic body below does not read the staged box
+                if (!done && mode != 1) {
+                    // ---- generic body (rare): per-pixel checks, sampling straight from global memory ----
+                    const float* plane = p.rgba + ((size_t)m * N + i) * 4 * tex;
+                    float* Rs = reinterpret_cast<float*>(R);
+                    const float* Ts = reinterpret_cast<const float*>(T);
+#pragma unroll
+                    for (int q = 0; q < kPix; ++q) {
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
+                        if (!coord_hits(tc.ix, tc.iy, fWt, fHt)) continue;
+                        const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
+                        const float fx = floorf(tc.ix), fy = floorf(tc.iy);
+                        const float wx1 = tc.ix - fx, wy1 = tc.iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+                        const float qv = fmaf(gq[q][0], sv.x, fmaf(gq[q][1], sv.y, fmaf(gq[q][2], sv.z, gq[q][3] * tc.scale)));
+                        const float d = qv - Rs[q];
+                        const float w = sv.w * Ts[q];
+                        Rs[q] = fmaf(sv.w, d, Rs[q]);
+                        scatter_pixel(gplane, tex, Wt, Ht, (int)fx, (int)fy, gq[q][0] * w, gq[q][1] * w, gq[q][2] * w, Ts[q] * d,
+                                      wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace gmpi

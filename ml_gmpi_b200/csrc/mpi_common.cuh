@@ -28,6 +28,8 @@ struct RenderParams {
     // frame index frame_offset + v instead of color/depth.  peer_frames is a device array of n_peers base pointers.
     float* const* peer_frames;
     int n_peers, frame_offset;
+    // training: transmittance before each plane, [V,N,H,W]; written by the forward, read by the staged backward (nullable)
+    float* transmittance;
 };
 
 // Store one finished pixel: plain outputs, or the same frame slot of every rank's gather buffer (NVLink peer stores).

@@ -238,6 +238,82 @@ __device__ __noinline__ float4 sample_plane_direct(const float* __restrict__ pla
 
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
 
+// Producer warp, shared by the forward (front-to-back) and backward (back-to-front) kernels: for every (tile, plane) of
+// this CTA, estimate the tile's texel footprint from its four corner rays, pick the narrowest box class, publish the stage
+// header and issue the TMA copies.
+template <bool kAlignCorners, bool kReverse>
+__device__ __forceinline__ void staged_producer(const RenderParams& p, const TmaMaps& maps, float* s_buf, StageMeta* s_meta,
+                                            uint64_t* s_full, uint64_t* s_empty, int tiles_x, int tiles_y, int lane) {
+    const int Ht = p.Ht, Wt = p.Wt, N = p.N;
+    const float fWt = (float)Wt, fHt = (float)Ht;
+    const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    const size_t img = (size_t)p.H * p.W;
+    const int tiles_per_view = tiles_x * tiles_y;
+    const int n_tiles = tiles_per_view * p.V;
+    if (lane < kNumMaps) tma_prefetch_desc(&maps.m[lane]);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int v = t / tiles_per_view, tt = t - v * tiles_per_view;
+        const int px0 = (tt % tiles_x) * kTileW, py0 = (tt / tiles_x) * kTileH;
+        const int m = __ldg(p.view2mpi + v);
+        const float* e = p.eye + 3 * v;
+        const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
+        const float zd[3] = {0.f, 0.f, 1.f};
+        // the four corner pixels of the tile (replicated over the warp), clamped into the image
+        const int cx = min(px0 + ((lane & 1) ? kTileW - 1 : 0), p.W - 1);
+        const int cy = min(py0 + ((lane & 2) ? kTileH - 1 : 0), p.H - 1);
+        const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)cy * p.W + cx;
+        const RayConst rc = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+        for (int ii = 0; ii < N; ++ii, ++it) {
+            const int i = kReverse ? N - 1 - ii : ii;
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            const PlaneConst pc = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
+            const TexCoord tc = plane_coord<kAlignCorners>(pc, rc, hsx, hsy, fWt, fHt);
+            // footprint of the tile = bounding box of the corner coordinates (the pixel -> texel map is projective,
+            // hence monotone along image rows and columns), +-1 texel of slack for rounding
+            const bool finite = fabsf(tc.ix) < 1e9f && fabsf(tc.iy) < 1e9f;
+            const bool all_finite = __all_sync(0xffffffffu, finite);
+            const int fx = finite ? (int)floorf(tc.ix) : 0, fy = finite ? (int)floorf(tc.iy) : 0;
+            const int xmin = __reduce_min_sync(0xffffffffu, fx), xmax = __reduce_max_sync(0xffffffffu, fx);
+            const int ymin = __reduce_min_sync(0xffffffffu, fy), ymax = __reduce_max_sync(0xffffffffu, fy);
+            // TMA needs a 16-byte aligned start in the innermost dimension: the box origin is a multiple of 4 texels
+            const int bx0 = ((xmin - 1) >> 2) << 2, by0 = ymin - 1;
+            const int need_w = xmax - bx0 + 3, need_h = ymax - ymin + 4;      // +1 east/south tap, +-1 slack
+            int mode = 0;
+            if (!all_finite || need_w > kMaxBW || ((need_h + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp > kMaxBH) mode = 2;   // would not fit a ring stage
+            else if (bx0 > Wt - 1 || bx0 + need_w - 1 < 0 || by0 > Ht - 1 || by0 + need_h - 1 < 0) mode = 1;
+            const int k = mode == 0 ? max(0, (need_w - kMinBW + kBWStep - 1) / kBWStep) : 0;
+            const int bw = kMinBW + k * kBWStep;
+            const int n_ops = mode == 0 ? (need_h + kRowsPerOp - 1) / kRowsPerOp : 0;
+            const int rows = n_ops * kRowsPerOp;
+            mbar_wait(&s_empty[s], ph ^ 1);
+            if (lane == 0) {
+                StageMeta mt;
+                mt.fbx0 = (float)bx0; mt.fby0 = (float)by0;
+                mt.rows2 = rows - 2;
+                mt.bw_mode = bw | (mode << 16);
+                s_meta[s] = mt;
+#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
+                mbar_arrive(&s_full[s]);                      // knock-out experiment: no TMA traffic at all
+#else
+                if (n_ops > 0) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16));
+                else mbar_arrive(&s_full[s]);
+#endif
+            }
+            __syncwarp();
+#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
+            if (false) {
+#else
+            if (lane < n_ops) {
+#endif
+                float* dst = s_buf + (size_t)s * kStageFloats + (size_t)lane * kRowsPerOp * 4 * bw;
+                tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
+            }
+        }
+    }
+}
+
 template <bool kAlignCorners>
 __global__ void __launch_bounds__(kStagedThreads, 1)
 mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
@@ -265,68 +341,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const int n_tiles = tiles_per_view * p.V;
 
     if (warp == kConsWarps) {
-        // ================================ producer warp ================================
-        if (lane < kNumMaps) tma_prefetch_desc(&maps.m[lane]);
-        uint32_t it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int v = t / tiles_per_view, tt = t - v * tiles_per_view;
-            const int px0 = (tt % tiles_x) * kTileW, py0 = (tt / tiles_x) * kTileH;
-            const int m = __ldg(p.view2mpi + v);
-            const float* e = p.eye + 3 * v;
-            const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
-            const float zd[3] = {0.f, 0.f, 1.f};
-            // the four corner pixels of the tile (replicated over the warp), clamped into the image
-            const int cx = min(px0 + ((lane & 1) ? kTileW - 1 : 0), p.W - 1);
-            const int cy = min(py0 + ((lane & 2) ? kTileH - 1 : 0), p.H - 1);
-            const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)cy * p.W + cx;
-            const RayConst rc = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
-            for (int i = 0; i < N; ++i, ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                const PlaneConst pc = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
-                const TexCoord tc = plane_coord<kAlignCorners>(pc, rc, hsx, hsy, fWt, fHt);
-                // footprint of the tile = bounding box of the corner coordinates (the pixel -> texel map is projective,
-                // hence monotone along image rows and columns), +-1 texel of slack for rounding
-                const bool finite = fabsf(tc.ix) < 1e9f && fabsf(tc.iy) < 1e9f;
-                const bool all_finite = __all_sync(0xffffffffu, finite);
-                const int fx = finite ? (int)floorf(tc.ix) : 0, fy = finite ? (int)floorf(tc.iy) : 0;
-                const int xmin = __reduce_min_sync(0xffffffffu, fx), xmax = __reduce_max_sync(0xffffffffu, fx);
-                const int ymin = __reduce_min_sync(0xffffffffu, fy), ymax = __reduce_max_sync(0xffffffffu, fy);
-                // TMA needs a 16-byte aligned start in the innermost dimension: the box origin is a multiple of 4 texels
-                const int bx0 = ((xmin - 1) >> 2) << 2, by0 = ymin - 1;
-                const int need_w = xmax - bx0 + 3, need_h = ymax - ymin + 4;      // +1 east/south tap, +-1 slack
-                int mode = 0;
-                if (!all_finite || need_w > kMaxBW || ((need_h + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp > kMaxBH) mode = 2;   // would not fit a ring stage
-                else if (bx0 > Wt - 1 || bx0 + need_w - 1 < 0 || by0 > Ht - 1 || by0 + need_h - 1 < 0) mode = 1;
-                const int k = mode == 0 ? max(0, (need_w - kMinBW + kBWStep - 1) / kBWStep) : 0;
-                const int bw = kMinBW + k * kBWStep;
-                const int n_ops = mode == 0 ? (need_h + kRowsPerOp - 1) / kRowsPerOp : 0;
-                const int rows = n_ops * kRowsPerOp;
-                mbar_wait(&s_empty[s], ph ^ 1);
-                if (lane == 0) {
-                    StageMeta mt;
-                    mt.fbx0 = (float)bx0; mt.fby0 = (float)by0;
-                    mt.rows2 = rows - 2;
-                    mt.bw_mode = bw | (mode << 16);
-                    s_meta[s] = mt;
-#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
-                    mbar_arrive(&s_full[s]);                      // knock-out experiment: no TMA traffic at all
-#else
-                    if (n_ops > 0) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16));
-                    else mbar_arrive(&s_full[s]);
-#endif
-                }
-                __syncwarp();
-#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
-                if (false) {
-#else
-                if (lane < n_ops) {
-#endif
-                    float* dst = s_buf + (size_t)s * kStageFloats + (size_t)lane * kRowsPerOp * 4 * bw;
-                    tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
-                }
-            }
-        }
+        staged_producer<kAlignCorners, false>(p, maps, s_buf, s_meta, s_full, s_empty, tiles_x, tiles_y, lane);
     } else {
         // ================================ consumer warps ================================
         // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them
@@ -403,6 +418,14 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 CoordPairs cc;
                 if (fast_c) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
 #endif
+                if (p.transmittance) {     // training: save T_i (before plane i) for the backward sweep, [V,N,H,W]
+                    float* ts = p.transmittance + ((size_t)v * N + i) * img;
+#pragma unroll
+                    for (int q = 0; q < kPix; ++q) {
+                        const int px = px0 + lane + 32 * (q & 1), py = py0 + kPairs * warp + (q >> 1);
+                        if (px < p.W && py < p.H) ts[(size_t)py * p.W + px] = (q & 1) ? T[q >> 1].y : T[q >> 1].x;
+                    }
+                }
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloats;

@@ -11,6 +11,7 @@
 #include "../../include/gmpi_mpi_render.h"
 #include "mpi_common.cuh"
 #include "mpi_fwd_staged.cuh"
+#include "mpi_bwd_staged.cuh"
 
 namespace gmpi {
 
@@ -83,6 +84,7 @@ mpi_fwd_direct_kernel(const RenderParams p) {
 #pragma unroll 2
         for (int i = 0; i < p.N; ++i, plane += 4 * tex) {
             const PlaneConst pc = s_pc[i];
+            if (p.transmittance) p.transmittance[((size_t)v * p.N + i) * img + pix] = T;   // training: T_i for the backward sweep
             const TexCoord tc = plane_coord<kAlignCorners>(pc, rc, hsx, hsy, fWt, fHt);
             if (check_last && i == p.N - 1) {
                 if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
@@ -356,8 +358,8 @@ const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
 
 static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
                            const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags,
-                           float* const* peer_frames, int n_peers, int frame_offset, int M, int V, int N, int Ht, int Wt,
-                           int H, int W, uint32_t options, void* stream) {
+                           float* const* peer_frames, int n_peers, int frame_offset, float* transmittance, int M, int V, int N,
+                           int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
     int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
     if (rc) return rc;
     if (!flags) return fail(GMPI_ERR_INVALID_ARGUMENT, "null flags pointer");
@@ -371,6 +373,7 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
     p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
     p.color = color; p.depth = depth; p.flags = flags;
     p.peer_frames = peer_frames; p.n_peers = n_peers; p.frame_offset = frame_offset;
+    p.transmittance = transmittance;
     p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
     cudaStream_t st = (cudaStream_t)stream;
     if (staged_eligible(V, N, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)) {
@@ -419,8 +422,17 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
 int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
                         const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags, int M,
                         int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
-    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags, nullptr, 0, 0, M, V, N, Ht, Wt, H, W,
-                           options, stream);
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags, nullptr, 0, 0, nullptr, M, V, N, Ht, Wt,
+                           H, W, options, stream);
+}
+
+int gmpi_mpi_render_fwd_train(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                              const float* eye, const float* z_dir, float* color, float* depth, float* transmittance,
+                              uint32_t* flags, int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options,
+                              void* stream) {
+    if (!transmittance) return fail(GMPI_ERR_INVALID_ARGUMENT, "null transmittance buffer");
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags, nullptr, 0, 0, transmittance, M, V, N, Ht,
+                           Wt, H, W, options, stream);
 }
 
 int gmpi_mpi_render_fwd_gather(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
@@ -429,7 +441,7 @@ int gmpi_mpi_render_fwd_gather(const float* rgba, const int32_t* view2mpi, const
                                uint32_t options, void* stream) {
     if (n_peers < 1) return fail(GMPI_ERR_INVALID_ARGUMENT, "n_peers must be >= 1");
     return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, nullptr, nullptr, flags, peer_frames, n_peers, frame_offset,
-                           M, V, N, Ht, Wt, H, W, options, stream);
+                           nullptr, M, V, N, Ht, Wt, H, W, options, stream);
 }
 
 int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
@@ -464,6 +476,46 @@ int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float*
     } else {
         GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mpi_bwd_direct_kernel<false><<<grid, block, smem, st>>>(p, tile_w, tile_h);
+    }
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                              const float* eye, const float* z_dir, const float* transmittance, const float* g_color,
+                              const float* g_depth, float* g_rgba, int M, int V, int N, int Ht, int Wt, int H, int W,
+                              uint32_t options, void* stream) {
+    int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
+    if (rc) return rc;
+    if (!g_color || !g_rgba || !transmittance) return fail(GMPI_ERR_INVALID_ARGUMENT, "null gradient / transmittance pointer");
+    // the staged sweep needs what the staged forward needs; otherwise the two-pass kernel recomputes the transmittance itself
+    if (!(staged_eligible(V, N, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)))
+        return gmpi_mpi_render_bwd(rgba, view2mpi, dhw, ray_dir, eye, z_dir, g_color, g_depth, g_rgba, M, V, N, Ht, Wt, H, W, options,
+                                   stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (options & GMPI_ZERO_GRAD)
+        GMPI_CUDA_OK(cudaMemsetAsync(g_rgba, 0, sizeof(float) * (size_t)M * N * 4 * Ht * Wt, st));
+    if (V == 0) return GMPI_OK;
+    TmaMaps maps;
+    for (int k = 0; k < kNumMaps; ++k)
+        if (encode_plane_map(&maps.m[k], rgba, (uint64_t)M * N, Ht, Wt, kMinBW + k * kBWStep, kRowsPerOp) != 0)
+            return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    RenderParams p{};
+    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
+    p.g_color = g_color; p.g_depth = g_depth; p.g_rgba = g_rgba; p.transmittance = const_cast<float*>(transmittance);
+    p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
+    int dev = 0, sms = 0;
+    GMPI_CUDA_OK(cudaGetDevice(&dev));
+    GMPI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+    const long n_tiles = (long)tiles_x * tiles_y * V;
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    if (options & GMPI_ALIGN_CORNERS) {
+        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+        mpi_bwd_staged_kernel<true><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+    } else {
+        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+        mpi_bwd_staged_kernel<false><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
     }
     GMPI_CUDA_OK(cudaGetLastError());
     return GMPI_OK;

@@ -37,19 +37,30 @@ class _RenderFn(torch.autograd.Function):
         V, _, H, W = ray_dir.shape
         color = torch.empty((V, 3, H, W), device=rgba.device, dtype=torch.float32)
         depth = torch.empty((V, 1, H, W), device=rgba.device, dtype=torch.float32)
+        # training: the forward also saves the transmittance in front of every plane (4 B per pixel-plane) so that the
+        # backward is ONE staged back-to-front sweep (torch autograd keeps ~30 such tensors alive for the reference)
+        trans = None
+        if ctx.needs_input_grad[0]:
+            trans = torch.empty((V, N, H, W), device=rgba.device, dtype=torch.float32)
         with torch.cuda.device(rgba.device):
-            _lib.check(lib.gmpi_mpi_render_fwd(
-                rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(),
-                z_dir.data_ptr(), color.data_ptr(), depth.data_ptr(), flags.data_ptr(),
-                M, V, N, Ht, Wt, H, W, options, _stream_ptr(rgba.device)))
-        ctx.save_for_backward(rgba, dhw, view2mpi, ray_dir, eye, z_dir)
+            if trans is not None:
+                _lib.check(lib.gmpi_mpi_render_fwd_train(
+                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
+                    color.data_ptr(), depth.data_ptr(), trans.data_ptr(), flags.data_ptr(),
+                    M, V, N, Ht, Wt, H, W, options, _stream_ptr(rgba.device)))
+            else:
+                _lib.check(lib.gmpi_mpi_render_fwd(
+                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(),
+                    z_dir.data_ptr(), color.data_ptr(), depth.data_ptr(), flags.data_ptr(),
+                    M, V, N, Ht, Wt, H, W, options, _stream_ptr(rgba.device)))
+        ctx.save_for_backward(rgba, dhw, view2mpi, ray_dir, eye, z_dir, trans)
         ctx.options = options
         ctx.set_materialize_grads(False)
         return color, depth
 
     @staticmethod
     def backward(ctx, g_color, g_depth):
-        rgba, dhw, view2mpi, ray_dir, eye, z_dir = ctx.saved_tensors
+        rgba, dhw, view2mpi, ray_dir, eye, z_dir, trans = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
             return (None,) * 8
         lib = _lib.load()
@@ -64,10 +75,16 @@ class _RenderFn(torch.autograd.Function):
             gd_ptr = g_depth.data_ptr()
         g_rgba = torch.empty_like(rgba)
         with torch.cuda.device(rgba.device):   # autograd worker threads do not inherit the device
-            _lib.check(lib.gmpi_mpi_render_bwd(
-                rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(),
-                z_dir.data_ptr(), g_color.data_ptr(), gd_ptr, g_rgba.data_ptr(),
-                M, V, N, Ht, Wt, H, W, ctx.options | _lib.OPT_ZERO_GRAD, _stream_ptr(rgba.device)))
+            if trans is not None:
+                _lib.check(lib.gmpi_mpi_render_bwd_saved(
+                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
+                    trans.data_ptr(), g_color.data_ptr(), gd_ptr, g_rgba.data_ptr(),
+                    M, V, N, Ht, Wt, H, W, ctx.options | _lib.OPT_ZERO_GRAD, _stream_ptr(rgba.device)))
+            else:
+                _lib.check(lib.gmpi_mpi_render_bwd(
+                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(),
+                    z_dir.data_ptr(), g_color.data_ptr(), gd_ptr, g_rgba.data_ptr(),
+                    M, V, N, Ht, Wt, H, W, ctx.options | _lib.OPT_ZERO_GRAD, _stream_ptr(rgba.device)))
         return g_rgba, None, None, None, None, None, None, None
 
 
