@@ -17,19 +17,33 @@ struct GradPairs {
     f2 g0[kPairs], g1[kPairs], g2[kPairs], gs[kPairs];   // upstream colour gradient and g_depth * (ray . z_dir)
 };
 
-// scatter one pixel's four channel gradients through its bilinear footprint with north-west texel (x0, y0)
-__device__ __forceinline__ void scatter_pixel(float* __restrict__ gplane, size_t tex, int Wt, int Ht, int x0, int y0, float v0, float v1,
-                                              float v2, float v3, float w00, float w01, float w10, float w11) {
-    const bool vx0 = (unsigned)x0 < (unsigned)Wt, vx1 = (unsigned)(x0 + 1) < (unsigned)Wt;
-    const bool vy0 = (unsigned)y0 < (unsigned)Ht, vy1 = (unsigned)(y0 + 1) < (unsigned)Ht;
-    float* b = gplane + ((long long)y0 * Wt + x0);
-    const float vals[4] = {v0, v1, v2, v3};
+// red.global.add.f32 without a return value; the predicated form compiles to one predicated REDG (no branch).
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_if(float* p, float v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
+}
+
+// Scatter one pixel's four channel gradients through its bilinear footprint with north-west texel (x0, y0)
+// (grid_sampler_2d_backward).  kAllValid: the caller proved (warp-uniformly) that all four taps are inside the texture.
+template <bool kAllValid>
+__device__ __forceinline__ void scatter_pixel(float* __restrict__ gplane, size_t tex, int Wt, int Ht, int x0, int y0, const float (&v)[4],
+                                              float w00, float w01, float w10, float w11) {
+    float* b0 = gplane + ((long long)y0 * Wt + x0);
+    float* b1 = b0 + Wt;
+    if (kAllValid) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c, b += tex) {
-        if (vx0 && vy0) atomicAdd(b, vals[c] * w00);
-        if (vx1 && vy0) atomicAdd(b + 1, vals[c] * w01);
-        if (vx0 && vy1) atomicAdd(b + Wt, vals[c] * w10);
-        if (vx1 && vy1) atomicAdd(b + Wt + 1, vals[c] * w11);
+        for (int c = 0; c < 4; ++c, b0 += tex, b1 += tex) {
+            red_add(b0, v[c] * w00); red_add(b0 + 1, v[c] * w01);
+            red_add(b1, v[c] * w10); red_add(b1 + 1, v[c] * w11);
+        }
+    } else {
+        const bool vx0 = (unsigned)x0 < (unsigned)Wt, vx1 = (unsigned)(x0 + 1) < (unsigned)Wt;
+        const bool vy0 = (unsigned)y0 < (unsigned)Ht, vy1 = (unsigned)(y0 + 1) < (unsigned)Ht;
+#pragma unroll
+        for (int c = 0; c < 4; ++c, b0 += tex, b1 += tex) {
+            red_add_if(b0, v[c] * w00, vx0 && vy0); red_add_if(b0 + 1, v[c] * w01, vx1 && vy0);
+            red_add_if(b1, v[c] * w10, vx0 && vy1); red_add_if(b1 + 1, v[c] * w11, vx1 && vy1);
+        }
     }
 }
 
@@ -76,8 +90,18 @@ __device__ __forceinline__ bool bwd_pairs(const float* __restrict__ sb, float fb
         const f2 ga = mul2(T[P], d);
         R[P] = fma2(a, d, R[P]);
         const f2 gr = mul2(G.g0[P], w), gg = mul2(G.g1[P], w), gb = mul2(G.g2[P], w);
-        scatter_pixel(gplane, tex, Wt, Ht, bx0 + rxa[P], by0 + rya[P], gr.x, gg.x, gb.x, ga.x, w00.x, w01.x, w10.x, w11.x);
-        scatter_pixel(gplane, tex, Wt, Ht, bx0 + rxb[P], by0 + ryb[P], gr.y, gg.y, gb.y, ga.y, w00.y, w01.y, w10.y, w11.y);
+        const int xa = bx0 + rxa[P], ya = by0 + rya[P], xb = bx0 + rxb[P], yb = by0 + ryb[P];
+        const float va[4] = {gr.x, gg.x, gb.x, ga.x}, vb[4] = {gr.y, gg.y, gb.y, ga.y};
+        // interior footprints (the common case) need no per-tap range checks: decide once per warp
+        const bool ok = (unsigned)xa < (unsigned)(Wt - 1) && (unsigned)ya < (unsigned)(Ht - 1) &&
+                        (unsigned)xb < (unsigned)(Wt - 1) && (unsigned)yb < (unsigned)(Ht - 1);
+        if (__all_sync(0xffffffffu, ok)) {
+            scatter_pixel<true>(gplane, tex, Wt, Ht, xa, ya, va, w00.x, w01.x, w10.x, w11.x);
+            scatter_pixel<true>(gplane, tex, Wt, Ht, xb, yb, vb, w00.y, w01.y, w10.y, w11.y);
+        } else {
+            scatter_pixel<false>(gplane, tex, Wt, Ht, xa, ya, va, w00.x, w01.x, w10.x, w11.x);
+            scatter_pixel<false>(gplane, tex, Wt, Ht, xb, yb, vb, w00.y, w01.y, w10.y, w11.y);
+        }
     }
     return true;
 }
@@ -87,7 +111,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1)
 mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_buf = reinterpret_cast<float*>(smem_raw);
-    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kStageFloats * 4);
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kStageFloatsBwd * 4);
     __shared__ StageMeta s_meta[kStages];
     __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
 
@@ -109,6 +133,7 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const int n_tiles = tiles_per_view * p.V;
 
     if (warp == kConsWarps) {
+        if (lane == 0) tma_prefetch_desc(&maps.t);
         staged_producer<kAlignCorners, true>(p, maps, s_buf, s_meta, s_full, s_empty, tiles_x, tiles_y, lane);
     } else {
         uint32_t it = 0;
@@ -167,15 +192,10 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             f2 R[kPairs];
 #pragma unroll
             for (int P = 0; P < kPairs; ++P) R[P] = splat(0.0f);
-            const float* tsv = p.transmittance + (size_t)v * N * img;
             for (int ii = 0; ii < N; ++ii, ++it) {
                 const int i = N - 1 - ii;
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
-                f2 T[kPairs];
-#pragma unroll
-                for (int P = 0; P < kPairs; ++P)      // saved by the forward; issued before the wait to hide the latency
-                    T[P] = make_float2(__ldg(tsv + (size_t)i * img + pix[2 * P]), __ldg(tsv + (size_t)i * img + pix[2 * P + 1]));
                 const PlaneConst pcc = s_pc[i];
                 const bool fast_c = warp_fast && pcc.fast != 0.0f;
                 CoordPairs cc;
@@ -183,8 +203,14 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 float* gplane = p.g_rgba + ((size_t)m * N + i) * 4 * tex;
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
-                const float* sb = s_buf + s * kStageFloats;
+                const float* sb = s_buf + s * kStageFloatsBwd;
                 const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
+                f2 T[kPairs];      // transmittance saved by the forward, staged next to the plane tile: [kTileH][kTileW]
+#pragma unroll
+                for (int P = 0; P < kPairs; ++P) {
+                    const float* tr = sb + kStageFloats + (kPairs * warp + P) * kTileW + lane;
+                    T[P] = make_float2(tr[0], tr[32]);
+                }
                 bool done = false;
                 if (fast_c && mode == 0) {
                     switch (bw) {   // warp-uniform
@@ -213,8 +239,8 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                         const float d = qv - Rs[q];
                         const float w = sv.w * Ts[q];
                         Rs[q] = fmaf(sv.w, d, Rs[q]);
-                        scatter_pixel(gplane, tex, Wt, Ht, (int)fx, (int)fy, gq[q][0] * w, gq[q][1] * w, gq[q][2] * w, Ts[q] * d,
-                                      wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
+                        const float vv[4] = {gq[q][0] * w, gq[q][1] * w, gq[q][2] * w, Ts[q] * d};
+                        scatter_pixel<false>(gplane, tex, Wt, Ht, (int)fx, (int)fy, vv, wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
                     }
                 }
             }

@@ -34,10 +34,13 @@ constexpr int kNumMaps = (kMaxBW - kMinBW) / kBWStep + 1;
 constexpr int kMaxPlanesStaged = 512;                  // plane-constant table: 32 B per plane in shared memory
 constexpr int kStageFloats = kMaxBW * kMaxBH * 4;
 constexpr size_t kStagedSmem = (size_t)kStages * kStageFloats * 4 + (size_t)kMaxPlanesStaged * 32;
+constexpr size_t kStagedSmemBwd = (size_t)kStages * (kStageFloats + kTileW * kTileH) * 4 + (size_t)kMaxPlanesStaged * 32;
 
 struct TmaMaps {
     CUtensorMap m[kNumMaps];
+    CUtensorMap t;      // backward only: saved transmittance [V*N][H][W], box {kTileW, kTileH, 1}
 };
+constexpr int kStageFloatsBwd = kStageFloats + kTileW * kTileH;   // backward stages also carry the tile's transmittance
 
 // per-stage header written by the producer before it arms the full barrier
 struct __align__(16) StageMeta {
@@ -244,6 +247,8 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 template <bool kAlignCorners, bool kReverse>
 __device__ __forceinline__ void staged_producer(const RenderParams& p, const TmaMaps& maps, float* s_buf, StageMeta* s_meta,
                                             uint64_t* s_full, uint64_t* s_empty, int tiles_x, int tiles_y, int lane) {
+    constexpr int kStride = kReverse ? kStageFloatsBwd : kStageFloats;      // floats per ring stage
+    constexpr uint32_t kTBytes = kReverse ? (uint32_t)(kTileW * kTileH * 4) : 0u;
     const int Ht = p.Ht, Wt = p.Wt, N = p.N;
     const float fWt = (float)Wt, fHt = (float)Ht;
     const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
@@ -297,8 +302,10 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
 #if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
                 mbar_arrive(&s_full[s]);                      // knock-out experiment: no TMA traffic at all
 #else
-                if (n_ops > 0) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16));
+                if (n_ops > 0 || kTBytes) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16) + kTBytes);
                 else mbar_arrive(&s_full[s]);
+                if (kReverse)   // the tile's saved transmittance for this plane rides in the same stage
+                    tma_load_3d(s_buf + (size_t)s * kStride + kStageFloats, &maps.t, &s_full[s], px0, py0, v * N + i);
 #endif
             }
             __syncwarp();
@@ -307,7 +314,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
 #else
             if (lane < n_ops) {
 #endif
-                float* dst = s_buf + (size_t)s * kStageFloats + (size_t)lane * kRowsPerOp * 4 * bw;
+                float* dst = s_buf + (size_t)s * kStride + (size_t)lane * kRowsPerOp * 4 * bw;
                 tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
             }
         }

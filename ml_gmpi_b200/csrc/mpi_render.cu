@@ -489,7 +489,8 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
     if (rc) return rc;
     if (!g_color || !g_rgba || !transmittance) return fail(GMPI_ERR_INVALID_ARGUMENT, "null gradient / transmittance pointer");
     // the staged sweep needs what the staged forward needs; otherwise the two-pass kernel recomputes the transmittance itself
-    if (!(staged_eligible(V, N, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31)))
+    if (!(staged_eligible(V, N, Ht, Wt, H, W) && ((uintptr_t)rgba & 15) == 0 && (size_t)M * N < ((size_t)1 << 31) && W % 4 == 0 &&
+          ((uintptr_t)transmittance & 15) == 0 && (size_t)V * N < ((size_t)1 << 31)))
         return gmpi_mpi_render_bwd(rgba, view2mpi, dhw, ray_dir, eye, z_dir, g_color, g_depth, g_rgba, M, V, N, Ht, Wt, H, W, options,
                                    stream);
     cudaStream_t st = (cudaStream_t)stream;
@@ -500,6 +501,8 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
     for (int k = 0; k < kNumMaps; ++k)
         if (encode_plane_map(&maps.m[k], rgba, (uint64_t)M * N, Ht, Wt, kMinBW + k * kBWStep, kRowsPerOp) != 0)
             return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (encode_slab_map(&maps.t, transmittance, (uint64_t)V * N, H, W, kTileW, kTileH, 1) != 0)
+        return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled (transmittance) failed");
     RenderParams p{};
     p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
     p.g_color = g_color; p.g_depth = g_depth; p.g_rgba = g_rgba; p.transmittance = const_cast<float*>(transmittance);
@@ -511,11 +514,11 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
     const long n_tiles = (long)tiles_x * tiles_y * V;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
     if (options & GMPI_ALIGN_CORNERS) {
-        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
-        mpi_bwd_staged_kernel<true><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmemBwd));
+        mpi_bwd_staged_kernel<true><<<grid, kStagedThreads, kStagedSmemBwd, st>>>(p, maps, tiles_x, tiles_y);
     } else {
-        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
-        mpi_bwd_staged_kernel<false><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+        GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmemBwd));
+        mpi_bwd_staged_kernel<false><<<grid, kStagedThreads, kStagedSmemBwd, st>>>(p, maps, tiles_x, tiles_y);
     }
     GMPI_CUDA_OK(cudaGetLastError());
     return GMPI_OK;
