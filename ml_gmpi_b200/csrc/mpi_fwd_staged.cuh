@@ -31,7 +31,14 @@ constexpr int kMaxBH = (((kTileH * 5) / 4 + 6 + kRowsPerOp - 1) / kRowsPerOp) * 
 // sixteen taps are LDS [reg + immediate]; the producer picks the narrowest class that covers the footprint.
 constexpr int kMinBW = 56, kBWStep = 8;
 constexpr int kNumMaps = (kMaxBW - kMinBW) / kBWStep + 1;
-constexpr int kMaxPlanesStaged = 512;                  // plane-constant table: 32 B per plane in shared memory
+#ifndef GMPI_MAX_PLANES_STAGED
+#define GMPI_MAX_PLANES_STAGED 512
+#endif
+#ifndef GMPI_CTAS_PER_SM
+#define GMPI_CTAS_PER_SM 1
+#endif
+constexpr int kMaxPlanesStaged = GMPI_MAX_PLANES_STAGED;   // plane-constant table: 32 B per plane in shared memory
+constexpr int kCtasPerSm = GMPI_CTAS_PER_SM;
 constexpr int kStageFloats = kMaxBW * kMaxBH * 4;
 constexpr size_t kStagedSmem = (size_t)kStages * kStageFloats * 4 + (size_t)kMaxPlanesStaged * 32;
 constexpr size_t kStagedSmemBwd = (size_t)kStages * (kStageFloats + kTileW * kTileH) * 4 + (size_t)kMaxPlanesStaged * 32;
@@ -322,7 +329,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
 }
 
 template <bool kAlignCorners>
-__global__ void __launch_bounds__(kStagedThreads, 1)
+__global__ void __launch_bounds__(kStagedThreads, kCtasPerSm)
 mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_buf = reinterpret_cast<float*>(smem_raw);   // the ring starts the dynamic segment (1024-byte aligned)

@@ -389,7 +389,7 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
             GMPI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
             const long n_tiles = (long)tiles_x * tiles_y * V;
-            const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+            const int grid = (int)(n_tiles < (long)sms * kCtasPerSm ? n_tiles : (long)sms * kCtasPerSm);
             if (options & GMPI_ALIGN_CORNERS) {
                 GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
                 mpi_fwd_staged_kernel<true><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
