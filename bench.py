@@ -346,6 +346,7 @@ def main():
                "steps": esteps, "ms_per_step": float(tt[0]) * 1e3, "api": "ml_gmpi_b200.host_api.render_host -> gmpi_mpi_render_fwd_host (C ABI)",
                "h2d_gbs": h2d / float(tt[0]) / 1e9}
         del h_rgba, oc, od
+        lib.gmpi_mpi_release_host_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

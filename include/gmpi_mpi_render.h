@@ -131,13 +131,16 @@ int gmpi_mpi_check_range(const float* rgba, int M, int N, int Ht, int Wt, uint32
  * Host-buffer forward (end-to-end entry point): all pointers are HOST memory (pinned memory
  * overlaps best).  Copies inputs to `device`, renders, copies colour/depth/flags back and
  * synchronises.  MPIs are streamed through a double-buffered device staging area so the copy of
- * MPI m+1 overlaps the render of MPI m.  *flags_out receives the OR of all flag bits.
+ * MPI m+1 overlaps the render of MPI m.  *flags_out receives the OR of all flag bits.  The staging buffers, streams and
+ * events are cached per device (grow-only) across calls; gmpi_mpi_release_host_cache() frees them.
  */
 int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const float* dhw,
                              const float* ray_dir, const float* eye, const float* z_dir,
                              float* color, float* depth, uint32_t* flags_out,
                              int M, int V, int N, int Ht, int Wt, int H, int W,
                              uint32_t options, int device);
+
+int gmpi_mpi_release_host_cache(void);
 
 /* Test hook: texel coordinates (ix, iy) of every (view, plane, pixel), out [V,N,2,H,W]; the
  * bit-exact stage of the path (must equal torch's fp32 op sequence, DESIGN.md "coordinates"). */

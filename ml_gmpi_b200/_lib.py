@@ -21,7 +21,7 @@ ABI_VERSION = 1
 
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
-    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed",
+    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed",
 ]
 
 _lib = None
@@ -62,6 +62,8 @@ def load():
     lib.gmpi_mpi_check_range.argtypes = [vp, i, i, i, i, vp, vp]
     lib.gmpi_mpi_render_fwd_host.restype = i
     lib.gmpi_mpi_render_fwd_host.argtypes = [vp] * 9 + [i] * 7 + [u32, i]
+    lib.gmpi_mpi_release_host_cache.restype = i
+    lib.gmpi_mpi_release_host_cache.argtypes = []
     lib.gmpi_debug_plane_coords.restype = i
     lib.gmpi_debug_plane_coords.argtypes = [vp] * 5 + [i] * 6 + [u32, vp]
     lib.gmpi_debug_plane_coords_packed.restype = i

@@ -1,13 +1,14 @@
 // Forward, TMA-staged persistent variant (the fast path).
 //
-// One CTA per SM walks (tile, plane) pairs: a 64x32-pixel output tile, planes front to back.  A producer warp
-// computes, from the tile's four corner rays, the texel footprint of the tile on the next plane and issues
-// cp.async.bulk.tensor copies of exactly that footprint (all four channels, row-chunks of kRowsPerOp) into a
-// 3-stage shared-memory ring; 16 consumer warps (4 pixels per thread) take their 16 bilinear taps per plane from
-// shared memory (conflict-free: a warp reads 32 consecutive x of one row) and composite in registers.
-// TMA's out-of-bounds zero fill implements padding_mode="zeros".  Every consumer thread verifies that its taps lie
-// inside the staged box and otherwise samples global memory directly, so results never depend on the footprint
-// estimate (arbitrary ray tensors stay correct, only slower).
+// One CTA per SM walks (tile, plane) pairs: a 64x30-pixel output tile, planes front to back.  A producer warp computes,
+// from the tile's four corner rays, the texel footprint of the tile on the next plane and issues cp.async.bulk.tensor
+// copies of exactly that footprint (all four channels, 4-row chunks, origin aligned to 16 bytes, width rounded up to one
+// of five compile-time classes) into a 3-stage shared-memory ring; 15 consumer warps (4 pixels = 2 packed f32x2 pairs per
+// thread) take their 16 bilinear taps per pixel and plane from shared memory (a warp reads 32 consecutive x of one row:
+// conflict-free while the texel/pixel scale is <= 1) and composite in registers.  TMA's out-of-bounds zero fill implements
+// padding_mode="zeros".  Every consumer thread verifies that its taps lie inside the staged box and otherwise samples
+// global memory directly, so results never depend on the footprint estimate (arbitrary ray tensors stay correct, only
+// slower).  DESIGN.md section 4.1 has the measurements and what bounds the kernel.
 #pragma once
 #include "mpi_common.cuh"
 #include "tma_utils.cuh"
@@ -174,11 +175,7 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float
     fma2(make_float2(ta[(4 + ch) * BW + 1], tb[(4 + ch) * BW + 1]), w11,                                       \
          fma2(make_float2(ta[(4 + ch) * BW], tb[(4 + ch) * BW]), w10,                                          \
               fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
-#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 1
-        const f2 r = GMPI_TAP(0), g = r, b = r, a = GMPI_TAP(3);   // knock-out experiment: half the LDS
-#else
         const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2), a = GMPI_TAP(3);
-#endif
 #undef GMPI_TAP
         const f2 w = mul2(a, T[P]);                     // mpi.py:423
         cr[P] = fma2(w, r, cr[P]);                      // mpi.py:430
@@ -186,54 +183,6 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float
         cb[P] = fma2(w, b, cb[P]);
         cws[P] = fma2(w, c.sc[P], cws[P]);              // depth_i = scale * (ray . z_dir), mpi.py:150
         T[P] = fma2(w, m1, T[P]);   // T(1-a); the reference's +1e-10 changes any later weight by < 1e-10 absolute
-    }
-    return true;
-}
-
-// Same with a run-time box width (one code body for every width; eight address adds per pixel instead of immediates).
-__device__ __forceinline__ bool sample_pairs_dyn(const float* __restrict__ sb, int bw, float fbx0, float fby0, int rows2, const CoordPairs& c,
-                                                 f2 (&T)[kPairs], f2 (&cr)[kPairs], f2 (&cg)[kPairs], f2 (&cb)[kPairs], f2 (&cws)[kPairs]) {
-    const f2 m1 = splat(-1.0f), one = splat(1.0f), nbx = splat(-fbx0), nby = splat(-fby0);
-    f2 fx0[kPairs], fy0[kPairs];
-    int ia[kPairs], ib[kPairs];
-    bool inbox = true;
-    const int bw4 = 4 * bw;
-    const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
-    const int cx = kFloorMagicBits + (int)fbx0, cy = kFloorMagicBits + (int)fby0;   // box origins are small integers
-    (void)nbx; (void)nby;
-#pragma unroll
-    for (int P = 0; P < kPairs; ++P) {
-        const f2 tx = add2_rm(c.ix[P], magic), ty = add2_rm(c.iy[P], magic);
-        fx0[P] = add2(tx, nmagic);                                    // floor as float (exact)
-        fy0[P] = add2(ty, nmagic);
-        const int rxa = __float_as_int(tx.x) - cx, rxb = __float_as_int(tx.y) - cx;   // floor - box origin, as integers
-        const int rya = __float_as_int(ty.x) - cy, ryb = __float_as_int(ty.y) - cy;
-        inbox = inbox && (unsigned)rxa <= (unsigned)(bw - 2) && (unsigned)rxb <= (unsigned)(bw - 2) &&
-                (unsigned)rya <= (unsigned)rows2 && (unsigned)ryb <= (unsigned)rows2;
-        ia[P] = rya * bw4 + rxa;
-        ib[P] = ryb * bw4 + rxb;
-    }
-    if (!inbox) return false;
-#pragma unroll
-    for (int P = 0; P < kPairs; ++P) {
-        const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);
-        const f2 wy0 = fma2(wy1, m1, one);
-        const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
-        const float* ta = sb + ia[P];
-        const float* tb = sb + ib[P];
-        f2 v[4];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            const float* a0 = ta + ch * bw; const float* b0 = tb + ch * bw;
-            v[ch] = fma2(make_float2(a0[bw4 + 1], b0[bw4 + 1]), w11,
-                         fma2(make_float2(a0[bw4], b0[bw4]), w10, fma2(make_float2(a0[1], b0[1]), w01, mul2(make_float2(a0[0], b0[0]), w00))));
-        }
-        const f2 w = mul2(v[3], T[P]);
-        cr[P] = fma2(w, v[0], cr[P]);
-        cg[P] = fma2(w, v[1], cg[P]);
-        cb[P] = fma2(w, v[2], cb[P]);
-        cws[P] = fma2(w, c.sc[P], cws[P]);
-        T[P] = fma2(w, m1, T[P]);
     }
     return true;
 }
@@ -306,21 +255,13 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
                 mt.rows2 = rows - 2;
                 mt.bw_mode = bw | (mode << 16);
                 s_meta[s] = mt;
-#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
-                mbar_arrive(&s_full[s]);                      // knock-out experiment: no TMA traffic at all
-#else
                 if (n_ops > 0 || kTBytes) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16) + kTBytes);
                 else mbar_arrive(&s_full[s]);
                 if (kReverse)   // the tile's saved transmittance for this plane rides in the same stage
                     tma_load_3d(s_buf + (size_t)s * kStride + kStageFloats, &maps.t, &s_full[s], px0, py0, v * N + i);
-#endif
             }
             __syncwarp();
-#if defined(GMPI_EXPERIMENT) && GMPI_EXPERIMENT == 3
-            if (false) {
-#else
             if (lane < n_ops) {
-#endif
                 float* dst = s_buf + (size_t)s * kStride + (size_t)lane * kRowsPerOp * 4 * bw;
                 tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
             }
@@ -328,7 +269,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
     }
 }
 
-template <bool kAlignCorners>
+template <bool kAlignCorners, bool kEmitT>
 __global__ void __launch_bounds__(kStagedThreads, kCtasPerSm)
 mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -409,30 +350,15 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
 #pragma unroll
             for (int P = 0; P < kPairs; ++P) { T[P] = splat(1.f); cr[P] = cg[P] = cb[P] = cws[P] = splat(0.f); }
             const float* plane = p.rgba + (size_t)m * N * 4 * tex;
-            // software pipeline: the coordinates of plane i+1 are computed while plane i's taps are in flight
-#ifndef GMPI_SWPIPE
-#define GMPI_SWPIPE 0   // measured: computing plane i+1 coordinates early costs registers and loses ~3%
-#endif
-            CoordPairs cn;
-            PlaneConst pcn = s_pc[0];
-            bool fast_n = warp_fast && pcn.fast != 0.0f;
-#if GMPI_SWPIPE
-            if (fast_n) coords_pairs<kAlignCorners>(pcn, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cn);
-#endif
+            // (computing plane i+1's coordinates ahead of the wait was measured: it costs registers and loses ~3 %)
             for (int i = 0; i < N; ++i, ++it, plane += 4 * tex) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
-#if GMPI_SWPIPE
-                const CoordPairs cc = cn;
-                const PlaneConst pcc = pcn;
-                const bool fast_c = fast_n;
-#else
                 const PlaneConst pcc = s_pc[i];
                 const bool fast_c = warp_fast && pcc.fast != 0.0f;
                 CoordPairs cc;
                 if (fast_c) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
-#endif
-                if (p.transmittance) {     // training: save T_i (before plane i) for the backward sweep, [V,N,H,W]
+                if (kEmitT) {              // training: save T_i (before plane i) for the backward sweep, [V,N,H,W]
                     float* ts = p.transmittance + ((size_t)v * N + i) * img;
 #pragma unroll
                     for (int q = 0; q < kPix; ++q) {
@@ -446,9 +372,6 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
                 bool done = false;
                 if (fast_c && mode == 0) {
-#if defined(GMPI_DYN_PITCH) && GMPI_DYN_PITCH
-                    done = sample_pairs_dyn(sb, bw, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws);
-#else
                     switch (bw) {   // warp-uniform
                         case 56: done = sample_pairs<56>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                         case 64: done = sample_pairs<64>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
@@ -456,14 +379,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                         case 80: done = sample_pairs<80>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                         default: done = sample_pairs<88>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
                     }
-#endif
                 }
-#if GMPI_SWPIPE
-                // next plane's constants and coordinates (independent of the staged data)
-                pcn = s_pc[min(i + 1, N - 1)];
-                fast_n = warp_fast && pcn.fast != 0.0f;
-                if (fast_n) coords_pairs<kAlignCorners>(pcn, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cn);
-#endif
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----
                     const int bw4 = 4 * bw;

@@ -390,13 +390,17 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
             const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
             const long n_tiles = (long)tiles_x * tiles_y * V;
             const int grid = (int)(n_tiles < (long)sms * kCtasPerSm ? n_tiles : (long)sms * kCtasPerSm);
-            if (options & GMPI_ALIGN_CORNERS) {
-                GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
-                mpi_fwd_staged_kernel<true><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
-            } else {
-                GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
-                mpi_fwd_staged_kernel<false><<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
-            }
+            auto launch = [&](auto kernel) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem);
+                if (e != cudaSuccess) return e;
+                kernel<<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+                return cudaSuccess;
+            };
+            const bool ac = (options & GMPI_ALIGN_CORNERS) != 0, emit = transmittance != nullptr;
+            if (ac && emit) GMPI_CUDA_OK(launch(mpi_fwd_staged_kernel<true, true>));
+            else if (ac) GMPI_CUDA_OK(launch(mpi_fwd_staged_kernel<true, false>));
+            else if (emit) GMPI_CUDA_OK(launch(mpi_fwd_staged_kernel<false, true>));
+            else GMPI_CUDA_OK(launch(mpi_fwd_staged_kernel<false, false>));
             GMPI_CUDA_OK(cudaGetLastError());
             return GMPI_OK;
         }
@@ -579,101 +583,123 @@ int gmpi_debug_division(const float* a, const float* b, float* out_fast, float* 
     return GMPI_OK;
 }
 
+// Per-device staging cache of the host-buffer entry point (grow-only; released by gmpi_mpi_release_host_cache or at exit):
+// two MPI slots (the copy of MPI m+1 overlaps the render of MPI m), per-view inputs/outputs, two streams, four events.
+struct HostCache {
+    float* mpi[2] = {nullptr, nullptr};
+    size_t mpi_bytes = 0;
+    void* misc = nullptr;           // dhw | ray | eye | z | color | depth | v2m | flags, carved from one allocation
+    size_t misc_bytes = 0;
+    cudaStream_t s_copy = nullptr, s_run = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+};
+static HostCache g_host_cache[64];
+
+static void host_cache_release(HostCache& c) {
+    for (int k = 0; k < 2; ++k) {
+        if (c.mpi[k]) cudaFree(c.mpi[k]);
+        if (c.ev_in[k]) cudaEventDestroy(c.ev_in[k]);
+        if (c.ev_free[k]) cudaEventDestroy(c.ev_free[k]);
+    }
+    if (c.misc) cudaFree(c.misc);
+    if (c.s_copy) cudaStreamDestroy(c.s_copy);
+    if (c.s_run) cudaStreamDestroy(c.s_run);
+    c = HostCache();
+}
+
+int gmpi_mpi_release_host_cache(void) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+        HostCache& c = g_host_cache[d];
+        if (!c.misc && !c.mpi[0] && !c.s_run) continue;
+        cudaSetDevice(d);
+        host_cache_release(c);
+    }
+    cudaSetDevice(cur);
+    return GMPI_OK;
+}
+
 int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
                              const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags_out,
                              int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options, int device) {
     int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
     if (rc) return rc;
     if (!color || !depth || !flags_out) return fail(GMPI_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (device < 0 || device >= 64) return fail(GMPI_ERR_INVALID_ARGUMENT, "device %d out of range", device);
     for (int v = 0; v + 1 < V; ++v)
         if (view2mpi[v] > view2mpi[v + 1]) return fail(GMPI_ERR_INVALID_ARGUMENT, "views must be MPI-major (sorted view2mpi)");
     for (int v = 0; v < V; ++v)
         if (view2mpi[v] < 0 || view2mpi[v] >= M) return fail(GMPI_ERR_INVALID_ARGUMENT, "view2mpi[%d]=%d out of range", v, view2mpi[v]);
     GMPI_CUDA_OK(cudaSetDevice(device));
+    HostCache& c = g_host_cache[device];
     const size_t tex = (size_t)Ht * Wt, img = (size_t)H * W;
     const size_t mpi_bytes = sizeof(float) * (size_t)N * 4 * tex;
-    // device staging: two MPI slots (copy of MPI m+1 overlaps the render of MPI m) + per-view data
-    float *d_mpi[2] = {nullptr, nullptr}, *d_dhw = nullptr, *d_ray = nullptr, *d_eye = nullptr, *d_z = nullptr;
-    float *d_color = nullptr, *d_depth = nullptr;
-    int32_t* d_v2m = nullptr;
-    uint32_t* d_flags = nullptr;
-    cudaStream_t s_copy = nullptr, s_run = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    int status = GMPI_OK;
-#define HOST_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess) {                                                                         \
-            status = fail(GMPI_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                \
-            goto done;                                                                                   \
-        }                                                                                                \
-    } while (0)
-    HOST_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    HOST_TRY(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
-        HOST_TRY(cudaMalloc(&d_mpi[k], mpi_bytes));
-        HOST_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        HOST_TRY(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
-    }
-    HOST_TRY(cudaMalloc(&d_dhw, sizeof(float) * (size_t)M * N * 3));
-    HOST_TRY(cudaMalloc(&d_ray, sizeof(float) * (size_t)V * 3 * img));
-    HOST_TRY(cudaMalloc(&d_eye, sizeof(float) * (size_t)V * 3));
-    HOST_TRY(cudaMalloc(&d_z, sizeof(float) * (size_t)V * 3));
-    HOST_TRY(cudaMalloc(&d_color, sizeof(float) * (size_t)V * 3 * img));
-    HOST_TRY(cudaMalloc(&d_depth, sizeof(float) * (size_t)V * img));
-    HOST_TRY(cudaMalloc(&d_v2m, sizeof(int32_t) * (size_t)(V > 0 ? V : 1)));
-    HOST_TRY(cudaMalloc(&d_flags, sizeof(uint32_t)));
-    HOST_TRY(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), s_run));
-    HOST_TRY(cudaMemsetAsync(d_v2m, 0, sizeof(int32_t) * (size_t)(V > 0 ? V : 1), s_run));   // staged MPI is slot-local index 0
-    HOST_TRY(cudaMemcpyAsync(d_dhw, dhw, sizeof(float) * (size_t)M * N * 3, cudaMemcpyHostToDevice, s_run));
-    HOST_TRY(cudaMemcpyAsync(d_ray, ray_dir, sizeof(float) * (size_t)V * 3 * img, cudaMemcpyHostToDevice, s_run));
-    HOST_TRY(cudaMemcpyAsync(d_eye, eye, sizeof(float) * (size_t)V * 3, cudaMemcpyHostToDevice, s_run));
-    HOST_TRY(cudaMemcpyAsync(d_z, z_dir, sizeof(float) * (size_t)V * 3, cudaMemcpyHostToDevice, s_run));
-    {
-        int v0 = 0, slot = 0, used[2] = {0, 0};
-        for (int m = 0; m < M; ++m) {
-            int v1 = v0;
-            while (v1 < V && view2mpi[v1] == m) ++v1;
-            if (v1 == v0) continue;
-            if (used[slot]) HOST_TRY(cudaStreamWaitEvent(s_copy, ev_free[slot], 0));
-            HOST_TRY(cudaMemcpyAsync(d_mpi[slot], rgba + (size_t)m * N * 4 * tex, mpi_bytes, cudaMemcpyHostToDevice, s_copy));
-            HOST_TRY(cudaEventRecord(ev_in[slot], s_copy));
-            HOST_TRY(cudaStreamWaitEvent(s_run, ev_in[slot], 0));
-            // mpi.py:70 compares against view 0's eye: pass views [v0,v1) with their own eye; the
-            // plane-behind-eye flag is evaluated against the first view of each launch.
-            status = gmpi_mpi_render_fwd(d_mpi[slot], d_v2m, d_dhw + (size_t)m * N * 3, d_ray + (size_t)v0 * 3 * img,
-                                         d_eye + (size_t)v0 * 3, d_z + (size_t)v0 * 3, d_color + (size_t)v0 * 3 * img,
-                                         d_depth + (size_t)v0 * img, d_flags, 1, v1 - v0, N, Ht, Wt, H, W, options, s_run);
-            if (status) goto done;
-            HOST_TRY(cudaEventRecord(ev_free[slot], s_run));
-            used[slot] = 1;
-            slot ^= 1;
-            v0 = v1;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_dhw = 0, o_ray = o_dhw + up(sizeof(float) * (size_t)M * N * 3), o_eye = o_ray + up(sizeof(float) * (size_t)V * 3 * img),
+                 o_z = o_eye + up(sizeof(float) * (size_t)V * 3), o_color = o_z + up(sizeof(float) * (size_t)V * 3),
+                 o_depth = o_color + up(sizeof(float) * (size_t)V * 3 * img), o_v2m = o_depth + up(sizeof(float) * (size_t)V * img),
+                 o_flags = o_v2m + up(sizeof(int32_t) * (size_t)(V > 0 ? V : 1)), misc_bytes = o_flags + 256;
+    if (!c.s_run) {
+        GMPI_CUDA_OK(cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking));
+        GMPI_CUDA_OK(cudaStreamCreateWithFlags(&c.s_run, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            GMPI_CUDA_OK(cudaEventCreateWithFlags(&c.ev_in[k], cudaEventDisableTiming));
+            GMPI_CUDA_OK(cudaEventCreateWithFlags(&c.ev_free[k], cudaEventDisableTiming));
         }
     }
-    HOST_TRY(cudaMemcpyAsync(color, d_color, sizeof(float) * (size_t)V * 3 * img, cudaMemcpyDeviceToHost, s_run));
-    HOST_TRY(cudaMemcpyAsync(depth, d_depth, sizeof(float) * (size_t)V * img, cudaMemcpyDeviceToHost, s_run));
-    HOST_TRY(cudaMemcpyAsync(flags_out, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s_run));
-    HOST_TRY(cudaStreamSynchronize(s_run));
-    HOST_TRY(cudaStreamSynchronize(s_copy));
-done:
-#undef HOST_TRY
-    for (int k = 0; k < 2; ++k) {
-        if (d_mpi[k]) cudaFree(d_mpi[k]);
-        if (ev_in[k]) cudaEventDestroy(ev_in[k]);
-        if (ev_free[k]) cudaEventDestroy(ev_free[k]);
+    if (c.mpi_bytes < mpi_bytes) {
+        for (int k = 0; k < 2; ++k) {
+            if (c.mpi[k]) GMPI_CUDA_OK(cudaFree(c.mpi[k]));
+            c.mpi[k] = nullptr;
+        }
+        c.mpi_bytes = 0;
+        for (int k = 0; k < 2; ++k) GMPI_CUDA_OK(cudaMalloc(&c.mpi[k], mpi_bytes));
+        c.mpi_bytes = mpi_bytes;
     }
-    if (d_dhw) cudaFree(d_dhw);
-    if (d_ray) cudaFree(d_ray);
-    if (d_eye) cudaFree(d_eye);
-    if (d_z) cudaFree(d_z);
-    if (d_color) cudaFree(d_color);
-    if (d_depth) cudaFree(d_depth);
-    if (d_v2m) cudaFree(d_v2m);
-    if (d_flags) cudaFree(d_flags);
-    if (s_copy) cudaStreamDestroy(s_copy);
-    if (s_run) cudaStreamDestroy(s_run);
-    return status;
+    if (c.misc_bytes < misc_bytes) {
+        if (c.misc) GMPI_CUDA_OK(cudaFree(c.misc));
+        c.misc = nullptr; c.misc_bytes = 0;
+        GMPI_CUDA_OK(cudaMalloc(&c.misc, misc_bytes));
+        c.misc_bytes = misc_bytes;
+    }
+    char* base = static_cast<char*>(c.misc);
+    float *d_dhw = (float*)(base + o_dhw), *d_ray = (float*)(base + o_ray), *d_eye = (float*)(base + o_eye), *d_z = (float*)(base + o_z);
+    float *d_color = (float*)(base + o_color), *d_depth = (float*)(base + o_depth);
+    int32_t* d_v2m = (int32_t*)(base + o_v2m);
+    uint32_t* d_flags = (uint32_t*)(base + o_flags);
+    cudaStream_t s_copy = c.s_copy, s_run = c.s_run;
+    GMPI_CUDA_OK(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), s_run));
+    GMPI_CUDA_OK(cudaMemsetAsync(d_v2m, 0, sizeof(int32_t) * (size_t)(V > 0 ? V : 1), s_run));   // a staged MPI is slot-local index 0
+    GMPI_CUDA_OK(cudaMemcpyAsync(d_dhw, dhw, sizeof(float) * (size_t)M * N * 3, cudaMemcpyHostToDevice, s_run));
+    GMPI_CUDA_OK(cudaMemcpyAsync(d_ray, ray_dir, sizeof(float) * (size_t)V * 3 * img, cudaMemcpyHostToDevice, s_run));
+    GMPI_CUDA_OK(cudaMemcpyAsync(d_eye, eye, sizeof(float) * (size_t)V * 3, cudaMemcpyHostToDevice, s_run));
+    GMPI_CUDA_OK(cudaMemcpyAsync(d_z, z_dir, sizeof(float) * (size_t)V * 3, cudaMemcpyHostToDevice, s_run));
+    int v0 = 0, slot = 0, used[2] = {0, 0};
+    for (int m = 0; m < M; ++m) {
+        int v1 = v0;
+        while (v1 < V && view2mpi[v1] == m) ++v1;
+        if (v1 == v0) continue;
+        if (used[slot]) GMPI_CUDA_OK(cudaStreamWaitEvent(s_copy, c.ev_free[slot], 0));
+        GMPI_CUDA_OK(cudaMemcpyAsync(c.mpi[slot], rgba + (size_t)m * N * 4 * tex, mpi_bytes, cudaMemcpyHostToDevice, s_copy));
+        GMPI_CUDA_OK(cudaEventRecord(c.ev_in[slot], s_copy));
+        GMPI_CUDA_OK(cudaStreamWaitEvent(s_run, c.ev_in[slot], 0));
+        // mpi.py:70 compares every distance with view 0's eye; here: with the first view of each MPI's launch
+        rc = gmpi_mpi_render_fwd(c.mpi[slot], d_v2m, d_dhw + (size_t)m * N * 3, d_ray + (size_t)v0 * 3 * img, d_eye + (size_t)v0 * 3,
+                                 d_z + (size_t)v0 * 3, d_color + (size_t)v0 * 3 * img, d_depth + (size_t)v0 * img, d_flags, 1, v1 - v0, N,
+                                 Ht, Wt, H, W, options, s_run);
+        if (rc) return rc;
+        GMPI_CUDA_OK(cudaEventRecord(c.ev_free[slot], s_run));
+        used[slot] = 1;
+        slot ^= 1;
+        v0 = v1;
+    }
+    GMPI_CUDA_OK(cudaMemcpyAsync(color, d_color, sizeof(float) * (size_t)V * 3 * img, cudaMemcpyDeviceToHost, s_run));
+    GMPI_CUDA_OK(cudaMemcpyAsync(depth, d_depth, sizeof(float) * (size_t)V * img, cudaMemcpyDeviceToHost, s_run));
+    GMPI_CUDA_OK(cudaMemcpyAsync(flags_out, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s_run));
+    GMPI_CUDA_OK(cudaStreamSynchronize(s_run));
+    GMPI_CUDA_OK(cudaStreamSynchronize(s_copy));
+    return GMPI_OK;
 }
 
 }  // extern "C"

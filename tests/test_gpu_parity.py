@@ -180,6 +180,12 @@ def test_host_buffer_entry_point():
     _lib.check(lib.gmpi_mpi_render_fwd_host(p(rgba), p(v2m), p(dhw), p(ray), p(eye), p(z), p(color), p(depth), p(flags),
                                             M, V, N, Ht, Wt, H, W, _lib.OPT_ALIGN_CORNERS, 0))
     assert rel_err(color, gd["color"]) <= EXPECT and rel_err(depth, gd["depth"]) <= EXPECT
+    # second call reuses the cached staging buffers; then they are released
+    color2, depth2 = np.empty_like(color), np.empty_like(depth)
+    _lib.check(lib.gmpi_mpi_render_fwd_host(p(rgba), p(v2m), p(dhw), p(ray), p(eye), p(z), p(color2), p(depth2), p(flags),
+                                            M, V, N, Ht, Wt, H, W, _lib.OPT_ALIGN_CORNERS, 0))
+    assert np.array_equal(color, color2) and np.array_equal(depth, depth2)
+    _lib.check(lib.gmpi_mpi_release_host_cache())
 
 
 # ------------------------------------------------------------------------------------------------
