@@ -163,7 +163,8 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
         if (lane == 0) tma_prefetch_desc(&maps.t);
         staged_producer<kAlignCorners, true>(p, maps, s_buf, s_meta, s_full, s_empty, tiles_x, tiles_y, lane);
     } else {
-        uint32_t it = 0;
+        int c_stage = 0;
+        uint32_t c_phase = 0;
         const size_t tex = (size_t)Ht * Wt;
         const float gscale = (p.options & GMPI_COLOR_MINUS1_1) ? 2.0f : 1.0f;   // upstream gradient is w.r.t. 2*color-1
         int v_table = -1;
@@ -219,10 +220,11 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             f2 R[kPairs];
 #pragma unroll
             for (int P = 0; P < kPairs; ++P) R[P] = splat(0.0f);
-            for (int ii = 0; ii < N; ++ii, ++it) {
+            for (int ii = 0; ii < N; ++ii) {
                 const int i = N - 1 - ii;
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
+                const int s = c_stage;
+                const uint32_t ph = c_phase;
+                if (++c_stage == kStages) { c_stage = 0; c_phase ^= 1u; }
                 const PlaneConst pcc = s_pc[i];
                 const bool fast_c = warp_fast && pcc.fast != 0.0f;
                 CoordPairs cc;
@@ -257,7 +259,9 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     const float* Ts = reinterpret_cast<const float*>(T);
 #pragma unroll
                     for (int q = 0; q < kPix; ++q) {
-                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
+                        RayConst rg = rc[q];
+                        rg.fast = false;
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
                         if (!coord_hits(tc.ix, tc.iy, fWt, fHt)) continue;
                         const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);

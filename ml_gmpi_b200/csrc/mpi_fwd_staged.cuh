@@ -212,7 +212,8 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
     const int tiles_per_view = tiles_x * tiles_y;
     const int n_tiles = tiles_per_view * p.V;
     if (lane < kNumMaps) tma_prefetch_desc(&maps.m[lane]);
-    uint32_t it = 0;
+    int p_stage = 0;
+    uint32_t p_phase = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int v = t / tiles_per_view, tt = t - v * tiles_per_view;
         const int px0 = (tt % tiles_x) * kTileW, py0 = (tt / tiles_x) * kTileH;
@@ -225,10 +226,11 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
         const int cy = min(py0 + ((lane & 2) ? kTileH - 1 : 0), p.H - 1);
         const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)cy * p.W + cx;
         const RayConst rc = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
-        for (int ii = 0; ii < N; ++ii, ++it) {
+        for (int ii = 0; ii < N; ++ii) {
             const int i = kReverse ? N - 1 - ii : ii;
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
+            const int s = p_stage;
+            const uint32_t ph = p_phase;
+            if (++p_stage == kStages) { p_stage = 0; p_phase ^= 1u; }
             const PlaneConst pc = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
             const TexCoord tc = plane_coord<kAlignCorners>(pc, rc, hsx, hsy, fWt, fHt);
             // footprint of the tile = bounding box of the corner coordinates (the pixel -> texel map is projective,
@@ -302,7 +304,8 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
         // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them
         const bool check_last = (p.options & GMPI_CHECK_LAST_PLANE) != 0;
         const bool minus1_1 = (p.options & GMPI_COLOR_MINUS1_1) != 0;
-        uint32_t it = 0;
+        int c_stage = 0;            // ring position of this warp: stage index and mbarrier phase parity
+        uint32_t c_phase = 0;
         uint32_t flag = 0;
         if (blockIdx.x == 0) {          // mpi.py:70: every plane distance against view 0's eye
             const float eye0_z = __ldg(p.eye + 2);
@@ -351,9 +354,10 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             for (int P = 0; P < kPairs; ++P) { T[P] = splat(1.f); cr[P] = cg[P] = cb[P] = cws[P] = splat(0.f); }
             const float* plane = p.rgba + (size_t)m * N * 4 * tex;
             // (computing plane i+1's coordinates ahead of the wait was measured: it costs registers and loses ~3 %)
-            for (int i = 0; i < N; ++i, ++it, plane += 4 * tex) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
+            for (int i = 0; i < N; ++i, plane += 4 * tex) {
+                const int s = c_stage;
+                const uint32_t ph = c_phase;
+                if (++c_stage == kStages) { c_stage = 0; c_phase ^= 1u; }
                 const PlaneConst pcc = s_pc[i];
                 const bool fast_c = warp_fast && pcc.fast != 0.0f;
                 CoordPairs cc;
@@ -391,7 +395,9 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     float* cwss = reinterpret_cast<float*>(cws);
 #pragma unroll
                     for (int q = 0; q < kPix; ++q) {
-                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
+                        RayConst rg = rc[q];
+                        rg.fast = false;            // rare path: plain IEEE divisions, no per-plane range checks in the hot loop
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);
                         const float rxx = fx - mt.fbx0, ryy = fy - mt.fby0;
                         float r, g, b, a;
@@ -424,7 +430,9 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 if (check_last && i == N - 1) {     // assert_not_out_of_last_plane, mpi.py:103-109 (once per tile)
 #pragma unroll
                     for (int q = 0; q < kPix; ++q) {
-                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rc[q], hsx, hsy, fWt, fHt);
+                        RayConst rg = rc[q];
+                        rg.fast = false;
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
                         if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
                     }
                 }
