@@ -50,13 +50,12 @@ __device__ __forceinline__ void scatter_pixel(float* __restrict__ gplane, size_t
 // Fast body: four pixels (two packed pairs) from a staged box of compile-time width BW.  Returns false (nothing done) if
 // any footprint is not inside the box.
 template <int BW>
-__device__ __forceinline__ bool bwd_pairs(const float* __restrict__ sb, float fbx0, float fby0, int rows2, const CoordPairs& c,
+__device__ __forceinline__ bool bwd_pairs(const float* __restrict__ sb, int cx, int cy, int rows2, const CoordPairs& c,
                                           const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], float* __restrict__ gplane,
                                           size_t tex, int Wt, int Ht) {
     const f2 m1 = splat(-1.0f), one = splat(1.0f);
     const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
-    const int bx0 = (int)fbx0, by0 = (int)fby0;
-    const int cx = kFloorMagicBits + bx0, cy = kFloorMagicBits + by0;
+    const int bx0 = cx - kFloorMagicBits, by0 = cy - kFloorMagicBits;
     f2 fx0[kPairs], fy0[kPairs];
     int rxa[kPairs], rxb[kPairs], rya[kPairs], ryb[kPairs];
     bool inbox = true;
@@ -226,14 +225,13 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 const uint32_t ph = c_phase;
                 if (++c_stage == kStages) { c_stage = 0; c_phase ^= 1u; }
                 const PlaneConst pcc = s_pc[i];
-                const bool fast_c = warp_fast && pcc.fast != 0.0f;
                 CoordPairs cc;
-                if (fast_c) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
+                if (warp_fast) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
                 float* gplane = p.g_rgba + ((size_t)m * N + i) * 4 * tex;
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloatsBwd;
-                const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
+                const int cls = mt.sel >> 16, mode = (mt.sel >> 8) & 3;
                 f2 T[kPairs];      // transmittance saved by the forward, staged next to the plane tile: [kTileH][kTileW]
 #pragma unroll
                 for (int P = 0; P < kPairs; ++P) {
@@ -241,17 +239,15 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     T[P] = make_float2(tr[0], tr[32]);
                 }
                 bool done = false;
-                if (fast_c && mode == 0) {
-                    switch (bw) {   // warp-uniform
-                        case 56: done = bwd_pairs<56>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
-                        case 64: done = bwd_pairs<64>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
-                        case 72: done = bwd_pairs<72>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
-                        case 80: done = bwd_pairs<80>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
-                        default: done = bwd_pairs<88>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht); break;
-                    }
+                if (warp_fast && cls != kSelSlow) {   // warp-uniform
+                    if (cls == 2) done = bwd_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (cls == 1) done = bwd_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (cls == 3) done = bwd_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (cls == 0) done = bwd_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else done = bwd_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[s]);     // the generic body below does not read the staged box
+                mbar_arrive_if(&s_empty[s], lane == 0);     // the generic body below does not read the staged box
                 if (!done && mode != 1) {
                     // ---- generic body (rare): per-pixel checks, sampling straight from global memory ----
                     const float* plane = p.rgba + ((size_t)m * N + i) * 4 * tex;

@@ -52,10 +52,12 @@ constexpr int kStageFloatsBwd = kStageFloats + kTileW * kTileH;   // backward st
 
 // per-stage header written by the producer before it arms the full barrier
 struct __align__(16) StageMeta {
-    float fbx0, fby0;      // box origin (texel coordinates of smem element [0][.][0]) as floats
+    int cx, cy;            // box origin (texel coordinates of smem element [0][.][0]) + kFloorMagicBits: bits(x + 1.5*2^23, rounded
+                           // down) - cx is floor(x) relative to the box
     int rows2;             // staged rows - 2: a footprint with north-west tap (rx, ry) fits iff 0<=rx<=bw-2, 0<=ry<=rows-2
-    int bw_mode;           // staged width (row pitch = 4*bw floats) | mode << 16;
-                           // mode 0 staged, 1 nothing to sample (footprint misses the texture), 2 sample global memory directly
+    int sel;               // bits 0-7 staged width (row pitch = 4*bw floats), bits 8-9 mode (0 staged, 1 nothing under the
+                           // tile, 2 sample from global), bits 16-23 width class for the packed fast body or 0xff (not usable:
+                           // mode != 0, or plane constants outside the exact-division range)
 };
 
 // ---- packed dual-fp32 arithmetic (sm_100 FFMA2/FADD2/FMUL2): one issue slot for two pixels, IEEE rn per element ----
@@ -90,6 +92,7 @@ __device__ __forceinline__ f2 add2_rm(f2 a, f2 b) {
 }
 constexpr float kFloorMagic = 12582912.0f;        // 1.5 * 2^23
 constexpr int kFloorMagicBits = 0x4b400000;
+constexpr int kSelSlow = 0xff;
 
 // a / b correctly rounded with y = RN(1/b), nb = -b (div_by_rcp, two pixels at once)
 __device__ __forceinline__ f2 div2_by_rcp(f2 a, f2 nb, f2 y) {
@@ -142,15 +145,13 @@ __device__ __forceinline__ void coords_pairs(const PlaneConst& pc, const RayPair
 // Sample + composite the four pixels from a staged box of compile-time width BW.  Returns false (and changes nothing)
 // if any of the four footprints is not inside the box.
 template <int BW>
-__device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float fbx0, float fby0, int rows2, const CoordPairs& c,
+__device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, int cx, int cy, int rows2, const CoordPairs& c,
                                              f2 (&T)[kPairs], f2 (&cr)[kPairs], f2 (&cg)[kPairs], f2 (&cb)[kPairs], f2 (&cws)[kPairs]) {
-    const f2 m1 = splat(-1.0f), one = splat(1.0f), nbx = splat(-fbx0), nby = splat(-fby0);
+    const f2 m1 = splat(-1.0f), one = splat(1.0f);
     f2 fx0[kPairs], fy0[kPairs];
     int ia[kPairs], ib[kPairs];
     bool inbox = true;
     const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
-    const int cx = kFloorMagicBits + (int)fbx0, cy = kFloorMagicBits + (int)fby0;   // box origins are small integers
-    (void)nbx; (void)nby;
 #pragma unroll
     for (int P = 0; P < kPairs; ++P) {
         const f2 tx = add2_rm(c.ix[P], magic), ty = add2_rm(c.iy[P], magic);         // floor without the XU pipe
@@ -163,7 +164,7 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, float
         ia[P] = rya * (4 * BW) + rxa;                                 // [row][channel][x], compile-time pitch
         ib[P] = ryb * (4 * BW) + rxb;
     }
-    if (!inbox) return false;
+    if (!__all_sync(0xffffffffu, inbox)) return false;   // warp-uniform, so the caller's fallback needs no reconvergence scaffolding
 #pragma unroll
     for (int P = 0; P < kPairs; ++P) {
         const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);   // fractional parts (exact)
@@ -253,9 +254,9 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             mbar_wait(&s_empty[s], ph ^ 1);
             if (lane == 0) {
                 StageMeta mt;
-                mt.fbx0 = (float)bx0; mt.fby0 = (float)by0;
+                mt.cx = kFloorMagicBits + bx0; mt.cy = kFloorMagicBits + by0;
                 mt.rows2 = rows - 2;
-                mt.bw_mode = bw | (mode << 16);
+                mt.sel = bw | (mode << 8) | ((mode == 0 && pc.fast != 0.0f ? k : kSelSlow) << 16);
                 s_meta[s] = mt;
                 if (n_ops > 0 || kTBytes) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16) + kTBytes);
                 else mbar_arrive(&s_full[s]);
@@ -352,16 +353,14 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             f2 T[kPairs], cr[kPairs], cg[kPairs], cb[kPairs], cws[kPairs];
 #pragma unroll
             for (int P = 0; P < kPairs; ++P) { T[P] = splat(1.f); cr[P] = cg[P] = cb[P] = cws[P] = splat(0.f); }
-            const float* plane = p.rgba + (size_t)m * N * 4 * tex;
             // (computing plane i+1's coordinates ahead of the wait was measured: it costs registers and loses ~3 %)
-            for (int i = 0; i < N; ++i, plane += 4 * tex) {
+            for (int i = 0; i < N; ++i) {
                 const int s = c_stage;
                 const uint32_t ph = c_phase;
                 if (++c_stage == kStages) { c_stage = 0; c_phase ^= 1u; }
                 const PlaneConst pcc = s_pc[i];
-                const bool fast_c = warp_fast && pcc.fast != 0.0f;
                 CoordPairs cc;
-                if (fast_c) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
+                if (warp_fast) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);   // before the wait
                 if (kEmitT) {              // training: save T_i (before plane i) for the backward sweep, [V,N,H,W]
                     float* ts = p.transmittance + ((size_t)v * N + i) * img;
 #pragma unroll
@@ -373,21 +372,21 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloats;
-                const int bw = mt.bw_mode & 0xffff, mode = mt.bw_mode >> 16;
+                const int cls = mt.sel >> 16;            // warp-uniform; the producer already folded mode and plane range in
                 bool done = false;
-                if (fast_c && mode == 0) {
-                    switch (bw) {   // warp-uniform
-                        case 56: done = sample_pairs<56>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
-                        case 64: done = sample_pairs<64>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
-                        case 72: done = sample_pairs<72>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
-                        case 80: done = sample_pairs<80>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
-                        default: done = sample_pairs<88>(sb, mt.fbx0, mt.fby0, mt.rows2, cc, T, cr, cg, cb, cws); break;
-                    }
+                if (warp_fast && cls != kSelSlow) {      // most frequent classes first (FFHQ poses: 72 > 64 > 80 >> 56, 88)
+                    if (cls == 2) done = sample_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (cls == 1) done = sample_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (cls == 3) done = sample_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (cls == 0) done = sample_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else done = sample_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
                 }
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----
-                    const int bw4 = 4 * bw;
+                    const int bw = mt.sel & 0xff, mode = (mt.sel >> 8) & 3, bw4 = 4 * bw;
                     const float fbw2 = (float)(bw - 2), fbh2 = (float)mt.rows2;
+                    const float fbx0 = (float)(mt.cx - kFloorMagicBits), fby0 = (float)(mt.cy - kFloorMagicBits);
+                    const float* plane = p.rgba + ((size_t)m * N + i) * 4 * tex;
                     float* Ts = reinterpret_cast<float*>(T);
                     float* crs = reinterpret_cast<float*>(cr);
                     float* cgs = reinterpret_cast<float*>(cg);
@@ -399,7 +398,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                         rg.fast = false;            // rare path: plain IEEE divisions, no per-plane range checks in the hot loop
                         const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);
-                        const float rxx = fx - mt.fbx0, ryy = fy - mt.fby0;
+                        const float rxx = fx - fbx0, ryy = fy - fby0;
                         float r, g, b, a;
                         if (mode == 0 && rxx >= 0.0f && rxx <= fbw2 && ryy >= 0.0f && ryy <= fbh2) {
                             const float wx1 = tc.ix - fx, wy1 = tc.iy - fy;
@@ -426,15 +425,16 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[s]);
-                if (check_last && i == N - 1) {     // assert_not_out_of_last_plane, mpi.py:103-109 (once per tile)
+                mbar_arrive_if(&s_empty[s], lane == 0);     // predicated, no branch
+            }
+            if (check_last) {     // assert_not_out_of_last_plane, mpi.py:103-109 (once per tile)
+                const PlaneConst pcl = s_pc[N - 1];
 #pragma unroll
-                    for (int q = 0; q < kPix; ++q) {
-                        RayConst rg = rc[q];
-                        rg.fast = false;
-                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
-                        if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
-                    }
+                for (int q = 0; q < kPix; ++q) {
+                    RayConst rg = rc[q];
+                    rg.fast = false;
+                    const TexCoord tc = plane_coord<kAlignCorners>(pcl, rg, hsx, hsy, fWt, fHt);
+                    if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
                 }
             }
 #pragma unroll
