@@ -224,14 +224,14 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 const int s = c_stage;
                 const uint32_t ph = c_phase;
                 if (++c_stage == kStages) { c_stage = 0; c_phase ^= 1u; }
-                const PlaneConst pcc = s_pc[i];
+                const PlaneConst pcc = s_pc[i];    // (prefetching it one plane ahead, as the forward does, only adds spills here)
                 CoordPairs cc;
                 if (warp_fast) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
                 float* gplane = p.g_rgba + ((size_t)m * N + i) * 4 * tex;
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloatsBwd;
-                const int cls = mt.sel >> 16, mode = (mt.sel >> 8) & 3;
+                const int sel = mt.sel, mode = (sel >> 8) & 3;
                 f2 T[kPairs];      // transmittance saved by the forward, staged next to the plane tile: [kTileH][kTileW]
 #pragma unroll
                 for (int P = 0; P < kPairs; ++P) {
@@ -239,12 +239,12 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     T[P] = make_float2(tr[0], tr[32]);
                 }
                 bool done = false;
-                if (warp_fast && cls != kSelSlow) {   // warp-uniform
-                    if (cls == 2) done = bwd_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
-                    else if (cls == 1) done = bwd_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
-                    else if (cls == 3) done = bwd_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
-                    else if (cls == 0) done = bwd_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
-                    else done = bwd_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                if (warp_fast) {   // warp-uniform, one-hot class
+                    if (sel & (1 << 18)) done = bwd_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (sel & (1 << 17)) done = bwd_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (sel & (1 << 19)) done = bwd_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (sel & (1 << 16)) done = bwd_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
+                    else if (sel & (1 << 20)) done = bwd_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, gplane, tex, Wt, Ht);
                 }
                 __syncwarp();
                 mbar_arrive_if(&s_empty[s], lane == 0);     // the generic body below does not read the staged box

@@ -56,8 +56,9 @@ struct __align__(16) StageMeta {
                            // down) - cx is floor(x) relative to the box
     int rows2;             // staged rows - 2: a footprint with north-west tap (rx, ry) fits iff 0<=rx<=bw-2, 0<=ry<=rows-2
     int sel;               // bits 0-7 staged width (row pitch = 4*bw floats), bits 8-9 mode (0 staged, 1 nothing under the
-                           // tile, 2 sample from global), bits 16-23 width class for the packed fast body or 0xff (not usable:
-                           // mode != 0, or plane constants outside the exact-division range)
+                           // tile, 2 sample from global), bits 16-20 width class for the packed fast body, ONE-HOT (a chain of
+                           // single-bit tests, most frequent first, is shorter than a jump table), or 0 (not usable: mode != 0,
+                           // or plane constants outside the exact-division range)
 };
 
 // ---- packed dual-fp32 arithmetic (sm_100 FFMA2/FADD2/FMUL2): one issue slot for two pixels, IEEE rn per element ----
@@ -92,7 +93,7 @@ __device__ __forceinline__ f2 add2_rm(f2 a, f2 b) {
 }
 constexpr float kFloorMagic = 12582912.0f;        // 1.5 * 2^23
 constexpr int kFloorMagicBits = 0x4b400000;
-constexpr int kSelSlow = 0xff;
+constexpr int kSelSlow = 0;     // class field is one-hot (bit 16 + class); 0 = packed fast body not usable
 
 // a / b correctly rounded with y = RN(1/b), nb = -b (div_by_rcp, two pixels at once)
 __device__ __forceinline__ f2 div2_by_rcp(f2 a, f2 nb, f2 y) {
@@ -256,7 +257,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
                 StageMeta mt;
                 mt.cx = kFloorMagicBits + bx0; mt.cy = kFloorMagicBits + by0;
                 mt.rows2 = rows - 2;
-                mt.sel = bw | (mode << 8) | ((mode == 0 && pc.fast != 0.0f ? k : kSelSlow) << 16);
+                mt.sel = bw | (mode << 8) | ((mode == 0 && pc.fast != 0.0f ? (1 << k) : kSelSlow) << 16);
                 s_meta[s] = mt;
                 if (n_ops > 0 || kTBytes) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16) + kTBytes);
                 else mbar_arrive(&s_full[s]);
@@ -353,14 +354,17 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
             f2 T[kPairs], cr[kPairs], cg[kPairs], cb[kPairs], cws[kPairs];
 #pragma unroll
             for (int P = 0; P < kPairs; ++P) { T[P] = splat(1.f); cr[P] = cg[P] = cb[P] = cws[P] = splat(0.f); }
-            // (computing plane i+1's coordinates ahead of the wait was measured: it costs registers and loses ~3 %)
+            PlaneConst pc_next = s_pc[0];
             for (int i = 0; i < N; ++i) {
                 const int s = c_stage;
                 const uint32_t ph = c_phase;
                 if (++c_stage == kStages) { c_stage = 0; c_phase ^= 1u; }
-                const PlaneConst pcc = s_pc[i];
+                const PlaneConst pcc = pc_next;            // loaded one plane ahead: no shared-memory latency in front of the
+                pc_next = s_pc[min(i + 1, N - 1)];         // coordinate chain (+1.3 %)
                 CoordPairs cc;
-                if (warp_fast) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);   // before the wait
+                // Coordinates before the wait.  (Computing plane i+1's coordinates in the shadow of plane i's tap loads was
+                // measured twice: -3 to -4 %; warps in their arithmetic phase leave the shared-memory pipe to the others.)
+                if (warp_fast) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
                 if (kEmitT) {              // training: save T_i (before plane i) for the backward sweep, [V,N,H,W]
                     float* ts = p.transmittance + ((size_t)v * N + i) * img;
 #pragma unroll
@@ -372,14 +376,14 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloats;
-                const int cls = mt.sel >> 16;            // warp-uniform; the producer already folded mode and plane range in
+                const int sel = mt.sel;                  // warp-uniform; the producer already folded mode and plane range in
                 bool done = false;
-                if (warp_fast && cls != kSelSlow) {      // most frequent classes first (FFHQ poses: 72 > 64 > 80 >> 56, 88)
-                    if (cls == 2) done = sample_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (cls == 1) done = sample_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (cls == 3) done = sample_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (cls == 0) done = sample_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else done = sample_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                if (warp_fast) {                         // most frequent classes first (FFHQ poses: 72 > 64 > 80 >> 56, 88)
+                    if (sel & (1 << 18)) done = sample_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 17)) done = sample_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 19)) done = sample_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 16)) done = sample_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 20)) done = sample_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
                 }
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----
