@@ -140,9 +140,11 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kStageFloatsBwd * 4);
     __shared__ StageMeta s_meta[kStages];
     __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+    __shared__ TileWalk s_walk;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+        s_walk.init(tiles_x, p.H, p.V);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kConsWarps);
@@ -155,21 +157,19 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const float fWt = (float)Wt, fHt = (float)Ht;
     const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
     const size_t img = (size_t)p.H * p.W;
-    const int tiles_per_view = tiles_x * tiles_y;
-    const int n_tiles = tiles_per_view * p.V;
 
     if (warp == kConsWarps) {
         if (lane == 0) tma_prefetch_desc(&maps.t);
-        staged_producer<kAlignCorners, true>(p, maps, s_buf, s_meta, s_full, s_empty, tiles_x, tiles_y, lane);
+        staged_producer<kAlignCorners, true>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
     } else {
         int c_stage = 0;
         uint32_t c_phase = 0;
         const size_t tex = (size_t)Ht * Wt;
         const float gscale = (p.options & GMPI_COLOR_MINUS1_1) ? 2.0f : 1.0f;   // upstream gradient is w.r.t. 2*color-1
         int v_table = -1;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int v = t / tiles_per_view, tt = t - v * tiles_per_view;
-            const int px0 = (tt % tiles_x) * kTileW, py0 = (tt / tiles_x) * kTileH;
+        TileXY txy;
+        for (int j = 0; s_walk.at(j, txy); ++j) {
+            const int v = txy.v, px0 = txy.px0, py0 = txy.py0;
             const int m = __ldg(p.view2mpi + v);
             const float* e = p.eye + 3 * v;
             const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
@@ -179,6 +179,10 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 for (int i = threadIdx.x; i < N; i += kConsThreads) s_pc[i] = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
                 consumer_bar_sync();
                 v_table = v;
+            }
+            if (py0 + kPairs * warp >= p.H) {      // no row of this warp is inside the image (partial bottom tile)
+                consumer_idle_tile(s_full, s_empty, N, lane, c_stage, c_phase);
+                continue;
             }
             const float* rays = p.ray_dir + (size_t)v * 3 * img;
             RayConst rc[kPix];
