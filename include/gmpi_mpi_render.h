@@ -156,6 +156,11 @@ int gmpi_debug_plane_coords_packed(const int32_t* view2mpi, const float* dhw, co
 /* Test hook: force the forward kernel variant: 0 auto (default), 1 direct-gather, 2 TMA-staged. */
 int gmpi_debug_set_fwd_variant(int variant);
 
+/* Test hook (host only, no GPU work): the persistent kernels' tile order.  Writes the (view, px0, py0) of the tiles that
+ * CTA `cta` of a `grid`-CTA launch walks, in order, into out_v_px0_py0[3 * max_tiles]; returns their number (>= 0) or a
+ * negative GMPI_ERR_* code.  Tile size: 64 x 30 pixels. */
+int gmpi_debug_tile_walk(int H, int W, int V, int grid, int cta, int* out_v_px0_py0, int max_tiles);
+
 /* Test hook: out_fast[i] = the kernels' reciprocal+FMA division a[i]/b[i]; out_ieee[i] = div.rn.f32. */
 int gmpi_debug_division(const float* a, const float* b, float* out_fast, float* out_ieee, size_t n,
                         void* stream);

@@ -21,7 +21,7 @@ ABI_VERSION = 1
 
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
-    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed",
+    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed", "gmpi_debug_tile_walk",
 ]
 
 _lib = None
@@ -72,6 +72,8 @@ def load():
     lib.gmpi_debug_division.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.gmpi_debug_set_fwd_variant.restype = i
     lib.gmpi_debug_set_fwd_variant.argtypes = [i]
+    lib.gmpi_debug_tile_walk.restype = i
+    lib.gmpi_debug_tile_walk.argtypes = [i, i, i, i, i, vp, i]
     if lib.gmpi_abi_version() != ABI_VERSION:
         raise GmpiLibraryError(f"ABI mismatch: library {lib.gmpi_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

@@ -144,7 +144,7 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        s_walk.init(tiles_x, p.H, p.V);
+        s_walk.init(tiles_x, p.H, p.V, (int)blockIdx.x, (int)gridDim.x);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kConsWarps);

@@ -207,24 +207,26 @@ __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 
 struct TileXY { int v, px0, py0; };
 struct TileWalk {
     int tiles_x, full_rows, full_per_view, n_full, n_part;
+    int cta, grid;               // blockIdx.x, gridDim.x (members so that the host-side test hook runs the same code)
     int n1, p_start, p_step;     // this CTA: number of full tiles; first partial tile and stride (p_step == 0: none)
     // (lives in shared memory, filled by one thread: it is read once per tile and must not cost registers in the plane loop)
-    __device__ __forceinline__ void init(int tiles_x_, int H, int V) {
+    __host__ __device__ __forceinline__ void init(int tiles_x_, int H, int V, int cta_, int grid_) {
         tiles_x = tiles_x_;
+        cta = cta_; grid = grid_;
         full_rows = H / kTileH;
         full_per_view = tiles_x * full_rows;
         n_full = full_per_view * V;
         n_part = (H % kTileH) ? tiles_x * V : 0;
-        const int b = blockIdx.x, G = gridDim.x, r = n_full % G;
+        const int b = cta, G = grid, r = n_full % G;
         n1 = b < n_full ? (n_full - b + G - 1) / G : 0;
         if (r == 0) { p_start = b; p_step = G; }
         else if (b >= r) { p_start = b - r; p_step = G - r; }
         else { p_start = 0; p_step = 0; }
     }
     // j-th tile of this CTA; false when done
-    __device__ __forceinline__ bool at(int j, TileXY& r) const {
+    __host__ __device__ __forceinline__ bool at(int j, TileXY& r) const {
         if (j < n1) {
-            const int t = blockIdx.x + j * gridDim.x;
+            const int t = cta + j * grid;
             r.v = t / full_per_view;
             const int tt = t - r.v * full_per_view;
             r.px0 = (tt % tiles_x) * kTileW; r.py0 = (tt / tiles_x) * kTileH;
@@ -335,7 +337,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        s_walk.init(tiles_x, p.H, p.V);
+        s_walk.init(tiles_x, p.H, p.V, (int)blockIdx.x, (int)gridDim.x);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kConsWarps);

@@ -341,6 +341,20 @@ int gmpi_debug_set_fwd_variant(int variant) {
     return GMPI_OK;
 }
 
+// Host evaluation of the staged kernels' tile order (same TileWalk code): tiles of CTA `cta` in a grid of `grid` CTAs, as
+// (view, px0, py0) triples.  Returns the count, or a negative error.
+int gmpi_debug_tile_walk(int H, int W, int V, int grid, int cta, int* out_v_px0_py0, int max_tiles) {
+    if (H < 1 || W < 1 || V < 1 || grid < 1 || cta < 0 || cta >= grid || max_tiles < 0 || (max_tiles > 0 && !out_v_px0_py0))
+        return -fail(GMPI_ERR_INVALID_ARGUMENT, "gmpi_debug_tile_walk: bad argument");
+    TileWalk w;
+    w.init((W + kTileW - 1) / kTileW, H, V, cta, grid);
+    TileXY t;
+    int n = 0;
+    for (; w.at(n, t); ++n)
+        if (n < max_tiles) { out_v_px0_py0[3 * n] = t.v; out_v_px0_py0[3 * n + 1] = t.px0; out_v_px0_py0[3 * n + 2] = t.py0; }
+    return n;
+}
+
 // staged needs 16-byte row strides for the tensor map and enough tiles to fill the persistent grid
 static bool staged_eligible(int V, int N, int Ht, int Wt, int H, int W) {
     (void)Ht;
