@@ -367,7 +367,7 @@ static bool staged_eligible(int V, int N, int Ht, int Wt, int H, int W) {
 }
 
 const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
-    return staged_eligible(1 << 20, N, Ht, Wt, H, W) ? "fwd_staged_tma_64x32" : "fwd_direct_32x8";
+    return staged_eligible(1 << 20, N, Ht, Wt, H, W) ? "fwd_staged_tma_64x30" : "fwd_direct_32x8";
 }
 
 static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
