@@ -6,9 +6,10 @@
 // of five compile-time classes) into a 3-stage shared-memory ring; 15 consumer warps (4 pixels = 2 packed f32x2 pairs per
 // thread) take their 16 bilinear taps per pixel and plane from shared memory (a warp reads 32 consecutive x of one row:
 // conflict-free while the texel/pixel scale is <= 1) and composite in registers.  TMA's out-of-bounds zero fill implements
-// padding_mode="zeros".  Every consumer thread verifies that its taps lie inside the staged box and otherwise samples
-// global memory directly, so results never depend on the footprint estimate (arbitrary ray tensors stay correct, only
-// slower).  DESIGN.md section 4.1 has the measurements and what bounds the kernel.
+// padding_mode="zeros".  Every consumer warp verifies (one vote) that all its taps lie inside the staged box; otherwise it
+// takes the generic body, which checks each pixel and samples global memory where the box does not cover it, so results
+// never depend on the footprint estimate (arbitrary ray tensors stay correct, only slower).  Tiles are walked full-height
+// first, partial bottom tiles last (TileWalk).  DESIGN.md section 4.1 has the measurements and what bounds the kernel.
 #pragma once
 #include "mpi_common.cuh"
 #include "tma_utils.cuh"
