@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GMPI_ABI_VERSION 1
+#define GMPI_ABI_VERSION 2
 
 /* return codes */
 #define GMPI_OK 0
@@ -64,6 +64,21 @@ const char* gmpi_last_error(void);
 
 /* Name of the kernel variant a forward call with these shapes would launch (diagnostics). */
 const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W);
+
+/*
+ * Which forward/backward kernels a call with these shapes launches: GMPI_PLAN_STAGED (persistent TMA-staged kernels, the fast
+ * path) or GMPI_PLAN_DIRECT (one thread per pixel, any shape, several times slower).  *why (nullable) receives the GMPI_WHY_*
+ * bits of every reason the staged path is not taken, so a caller can surface the performance cliff instead of finding it in a
+ * profile.  rgba may be NULL (alignment unknown: not checked).
+ */
+#define GMPI_PLAN_DIRECT 1
+#define GMPI_PLAN_STAGED 2
+#define GMPI_WHY_TEX_WIDTH 1u    /* Wt % 4 != 0: rows are not 16-byte multiples, no tensor map                     */
+#define GMPI_WHY_FEW_TILES 2u    /* fewer than 120 tiles of 64x30 pixels over all views: the persistent grid would idle */
+#define GMPI_WHY_MANY_PLANES 4u  /* N > 512: the per-view plane-constant table does not fit next to the ring        */
+#define GMPI_WHY_ALIGNMENT 8u    /* rgba base not 16-byte aligned                                                   */
+#define GMPI_WHY_FORCED 16u      /* gmpi_debug_set_fwd_variant(1)                                                    */
+int gmpi_mpi_render_fwd_plan(int V, int N, int Ht, int Wt, int H, int W, const void* rgba, uint32_t* why);
 
 /*
  * Forward: replaces MPI.forward (mpi.py:308-436) for all V views in one launch.

@@ -17,11 +17,16 @@ OPT_CHECK_LAST_PLANE = 2
 OPT_COLOR_MINUS1_1 = 4
 OPT_ZERO_GRAD = 8
 
-ABI_VERSION = 1
+PLAN_DIRECT, PLAN_STAGED = 1, 2
+WHY = {1: "texture width is not a multiple of 4", 2: "fewer than 120 tiles of 64x30 pixels", 4: "more than 512 planes",
+       8: "rgba base pointer not 16-byte aligned", 16: "direct kernel forced by gmpi_debug_set_fwd_variant"}
+
+ABI_VERSION = 2
 
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
     "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed", "gmpi_debug_tile_walk",
+    "gmpi_mpi_render_fwd_plan",
 ]
 
 _lib = None
@@ -48,6 +53,8 @@ def load():
     lib.gmpi_last_error.argtypes = []
     lib.gmpi_mpi_render_fwd_variant.restype = ctypes.c_char_p
     lib.gmpi_mpi_render_fwd_variant.argtypes = [i] * 5
+    lib.gmpi_mpi_render_fwd_plan.restype = i
+    lib.gmpi_mpi_render_fwd_plan.argtypes = [i] * 6 + [vp, vp]
     lib.gmpi_mpi_render_fwd.restype = i
     lib.gmpi_mpi_render_fwd.argtypes = [vp] * 9 + [i] * 7 + [u32, vp]
     lib.gmpi_mpi_render_fwd_gather.restype = i

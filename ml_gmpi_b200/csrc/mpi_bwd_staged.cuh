@@ -235,7 +235,7 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
                 const float* sb = s_buf + s * kStageFloatsBwd;
-                const int sel = mt.sel, mode = (sel >> 8) & 3;
+                const int sel = mt.sel;
                 f2 T[kPairs];      // transmittance saved by the forward, staged next to the plane tile: [kTileH][kTileW]
 #pragma unroll
                 for (int P = 0; P < kPairs; ++P) {
@@ -252,8 +252,9 @@ mpi_bwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 }
                 __syncwarp();
                 mbar_arrive_if(&s_empty[s], lane == 0);     // the generic body below does not read the staged box
-                if (!done && mode != 1) {
-                    // ---- generic body (rare): per-pixel checks, sampling straight from global memory ----
+                if (!done) {
+                    // ---- generic body (rare): per-pixel checks, sampling straight from global memory.  Also taken when the
+                    // producer's corner-ray estimate says "nothing under the tile" (mode 1): that is a hint, never trusted ----
                     const float* plane = p.rgba + ((size_t)m * N + i) * 4 * tex;
                     float* Rs = reinterpret_cast<float*>(R);
                     const float* Ts = reinterpret_cast<const float*>(T);

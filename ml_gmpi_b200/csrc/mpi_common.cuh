@@ -15,6 +15,8 @@ struct RenderParams {
     const float* dhw;         // [M,N,3]
     const float* ray_dir;     // [V,3,H,W]
     const float* eye;         // [V,3]
+    const float* eye0;        // eye of the call's GLOBAL view 0 (mpi.py:70 compares every plane distance with it); == eye
+                              // unless a host-side wrapper splits one call into several launches
     const float* z_dir;       // [V,3]
     float* color;             // [V,3,H,W]
     float* depth;             // [V,1,H,W]
@@ -63,7 +65,8 @@ __device__ __forceinline__ bool in_safe_range(float x) {
 
 // a / b, correctly rounded, given y = RN(1/b): q0 = RN(a*y); r = a - q0*b (exact in an FMA);
 // q = RN(q0 + r*y).  (Markstein's theorem; verified exhaustively over all divisor mantissas
-// on the CPU and against __fdiv_rn on the GPU by tests/test_gpu_coords.py.)
+// on the CPU by tools/check_division.c and against __fdiv_rn on the GPU by
+// tests/test_gpu_parity.py::test_fast_division_equals_ieee_division.)
 __device__ __forceinline__ float div_by_rcp(float a, float b, float y) {
     const float q0 = __fmul_rn(a, y);
     const float r = __fmaf_rn(-q0, b, a);

@@ -363,7 +363,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
         uint32_t c_phase = 0;
         uint32_t flag = 0;
         if (blockIdx.x == 0) {          // mpi.py:70: every plane distance against view 0's eye
-            const float eye0_z = __ldg(p.eye + 2);
+            const float eye0_z = __ldg(p.eye0 + 2);
             for (int j = threadIdx.x; j < p.M * N; j += kConsThreads)
                 if (!(__ldg(p.dhw + (size_t)j * 3) >= eye0_z)) flag |= GMPI_FLAG_PLANE_BEHIND_EYE;
         }
@@ -471,7 +471,8 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                             g = fmaf(t1[bw + 1], w11, fmaf(t1[bw], w10, fmaf(t0[bw + 1], w01, t0[bw] * w00)));
                             b = fmaf(t1[2 * bw + 1], w11, fmaf(t1[2 * bw], w10, fmaf(t0[2 * bw + 1], w01, t0[2 * bw] * w00)));
                             a = fmaf(t1[3 * bw + 1], w11, fmaf(t1[3 * bw], w10, fmaf(t0[3 * bw + 1], w01, t0[3 * bw] * w00)));
-                        } else if (mode != 1 && coord_hits(tc.ix, tc.iy, fWt, fHt)) {
+                        } else if (coord_hits(tc.ix, tc.iy, fWt, fHt)) {   // mode 1 ("nothing under the tile") is only the
+                            // producer's corner-ray estimate: every pixel is still tested on its own
                             const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
                             r = sv.x; g = sv.y; b = sv.z; a = sv.w;
                         } else {

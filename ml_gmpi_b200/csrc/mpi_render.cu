@@ -8,6 +8,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/gmpi_mpi_render.h"
 #include "mpi_common.cuh"
 #include "mpi_fwd_staged.cuh"
@@ -54,7 +57,7 @@ mpi_fwd_direct_kernel(const RenderParams p) {
     const int m = __ldg(p.view2mpi + v);
     const int tid = threadIdx.y * kFwdTileW + threadIdx.x;
     const float* e = p.eye + 3 * v;
-    const float eye0_z = __ldg(p.eye + 2);   // mpi.py:70 compares every distance with view 0's eye
+    const float eye0_z = __ldg(p.eye0 + 2);  // mpi.py:70 compares every distance with view 0's eye
     uint32_t flag = 0;
     for (int i = tid; i < p.N; i += kFwdTileW * kFwdTileH) {
         const float* dp = p.dhw + ((size_t)m * p.N + i) * 3;
@@ -319,7 +322,6 @@ static int check_common(const void* rgba, const void* view2mpi, const void* dhw,
         return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes M=%d V=%d N=%d Ht=%d Wt=%d H=%d W=%d", M, V, N, Ht, Wt, H, W);
     if ((size_t)Ht * Wt > (size_t)0x7fffffff)
         return fail(GMPI_ERR_UNSUPPORTED, "texture of %dx%d texels exceeds 2^31 elements per channel", Ht, Wt);
-    if (V > 65535) return fail(GMPI_ERR_UNSUPPORTED, "V=%d views exceed one launch (65535); split the batch", V);
     return GMPI_OK;
 }
 
@@ -333,11 +335,11 @@ int gmpi_abi_version(void) { return GMPI_ABI_VERSION; }
 
 const char* gmpi_last_error(void) { return g_err; }
 
-static int g_fwd_variant = 0;   // 0 auto, 1 direct, 2 staged
+static std::atomic<int> g_fwd_variant{0};   // 0 auto, 1 direct, 2 staged (test hook; relaxed atomic: any thread may set it)
 
 int gmpi_debug_set_fwd_variant(int variant) {
     if (variant < 0 || variant > 2) return fail(GMPI_ERR_INVALID_ARGUMENT, "variant must be 0 (auto), 1 (direct) or 2 (staged)");
-    g_fwd_variant = variant;
+    g_fwd_variant.store(variant, std::memory_order_relaxed);
     return GMPI_OK;
 }
 
@@ -355,15 +357,27 @@ int gmpi_debug_tile_walk(int H, int W, int V, int grid, int cta, int* out_v_px0_
     return n;
 }
 
-// staged needs 16-byte row strides for the tensor map and enough tiles to fill the persistent grid
-static bool staged_eligible(int V, int N, int Ht, int Wt, int H, int W) {
+// staged needs 16-byte row strides for the tensor map and enough tiles to fill the persistent grid; `why` receives the
+// GMPI_WHY_* bits of every reason the TMA-staged kernel is NOT used (0 = staged)
+static bool staged_eligible(int V, int N, int Ht, int Wt, int H, int W, uint32_t* why = nullptr) {
     (void)Ht;
-    if (N > kMaxPlanesStaged) return false;
-    if (Wt % 4 != 0) return false;
-    if (g_fwd_variant == 2) return true;
-    if (g_fwd_variant == 1) return false;
+    uint32_t w = 0;
+    if (N > kMaxPlanesStaged) w |= GMPI_WHY_MANY_PLANES;
+    if (Wt % 4 != 0) w |= GMPI_WHY_TEX_WIDTH;
+    const int forced = g_fwd_variant.load(std::memory_order_relaxed);
+    if (forced == 1) w |= GMPI_WHY_FORCED;
     const long tiles = (long)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * V;
-    return tiles >= 120;
+    if (forced != 2 && tiles < 120) w |= GMPI_WHY_FEW_TILES;
+    if (why) *why = w;
+    return w == 0;
+}
+
+int gmpi_mpi_render_fwd_plan(int V, int N, int Ht, int Wt, int H, int W, const void* rgba, uint32_t* why) {
+    uint32_t w = 0;
+    staged_eligible(V, N, Ht, Wt, H, W, &w);
+    if (rgba && ((uintptr_t)rgba & 15) != 0) w |= GMPI_WHY_ALIGNMENT;
+    if (why) *why = w;
+    return w == 0 ? GMPI_PLAN_STAGED : GMPI_PLAN_DIRECT;
 }
 
 const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
@@ -371,7 +385,7 @@ const char* gmpi_mpi_render_fwd_variant(int N, int Ht, int Wt, int H, int W) {
 }
 
 static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
-                           const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags,
+                           const float* eye, const float* eye0, const float* z_dir, float* color, float* depth, uint32_t* flags,
                            float* const* peer_frames, int n_peers, int frame_offset, float* transmittance, int M, int V, int N,
                            int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
     int rc = check_common(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W);
@@ -384,7 +398,7 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
     }
     if (V == 0) return GMPI_OK;
     RenderParams p{};
-    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
+    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.eye0 = eye0 ? eye0 : eye; p.z_dir = z_dir;
     p.color = color; p.depth = depth; p.flags = flags;
     p.peer_frames = peer_frames; p.n_peers = n_peers; p.frame_offset = frame_offset;
     p.transmittance = transmittance;
@@ -396,7 +410,7 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
         for (int k = 0; k < kNumMaps && ok; ++k)
             ok = encode_plane_map(&maps.m[k], rgba, (uint64_t)M * N, Ht, Wt, kMinBW + k * kBWStep, kRowsPerOp) == 0;
         if (!ok) {
-            if (g_fwd_variant == 2) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+            if (g_fwd_variant.load(std::memory_order_relaxed) == 2) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         } else {
             int dev = 0, sms = 0;
             GMPI_CUDA_OK(cudaGetDevice(&dev));
@@ -424,6 +438,7 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
     dim3 block(kFwdTileW, kFwdTileH);
     dim3 grid((W + kFwdTileW - 1) / kFwdTileW, (H + kFwdTileH - 1) / kFwdTileH, V);
     if (grid.y > 65535) return fail(GMPI_ERR_UNSUPPORTED, "image height %d too large", H);
+    if (V > 65535) return fail(GMPI_ERR_UNSUPPORTED, "V=%d views exceed one launch of the direct kernel (65535); split the batch", V);
     if (options & GMPI_ALIGN_CORNERS) {
         if (smem > 48 * 1024)
             GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_fwd_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -440,7 +455,7 @@ static int render_fwd_impl(const float* rgba, const int32_t* view2mpi, const flo
 int gmpi_mpi_render_fwd(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
                         const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags, int M,
                         int V, int N, int Ht, int Wt, int H, int W, uint32_t options, void* stream) {
-    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags, nullptr, 0, 0, nullptr, M, V, N, Ht, Wt,
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, nullptr, z_dir, color, depth, flags, nullptr, 0, 0, nullptr, M, V, N, Ht, Wt,
                            H, W, options, stream);
 }
 
@@ -449,7 +464,7 @@ int gmpi_mpi_render_fwd_train(const float* rgba, const int32_t* view2mpi, const 
                               uint32_t* flags, int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options,
                               void* stream) {
     if (!transmittance) return fail(GMPI_ERR_INVALID_ARGUMENT, "null transmittance buffer");
-    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags, nullptr, 0, 0, transmittance, M, V, N, Ht,
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, nullptr, z_dir, color, depth, flags, nullptr, 0, 0, transmittance, M, V, N, Ht,
                            Wt, H, W, options, stream);
 }
 
@@ -458,7 +473,7 @@ int gmpi_mpi_render_fwd_gather(const float* rgba, const int32_t* view2mpi, const
                                int frame_offset, uint32_t* flags, int M, int V, int N, int Ht, int Wt, int H, int W,
                                uint32_t options, void* stream) {
     if (n_peers < 1) return fail(GMPI_ERR_INVALID_ARGUMENT, "n_peers must be >= 1");
-    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, z_dir, nullptr, nullptr, flags, peer_frames, n_peers, frame_offset,
+    return render_fwd_impl(rgba, view2mpi, dhw, ray_dir, eye, nullptr, z_dir, nullptr, nullptr, flags, peer_frames, n_peers, frame_offset,
                            nullptr, M, V, N, Ht, Wt, H, W, options, stream);
 }
 
@@ -474,7 +489,7 @@ int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float*
         GMPI_CUDA_OK(cudaMemsetAsync(g_rgba, 0, sizeof(float) * (size_t)M * N * 4 * Ht * Wt, st));
     if (V == 0) return GMPI_OK;
     RenderParams p{};
-    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
+    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.eye0 = eye; p.z_dir = z_dir;
     p.g_color = g_color; p.g_depth = g_depth; p.g_rgba = g_rgba;
     p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
     // tile: as many threads (<=128) as the per-thread transmittance stash allows
@@ -488,6 +503,7 @@ int gmpi_mpi_render_bwd(const float* rgba, const int32_t* view2mpi, const float*
     dim3 block(tile_w, tile_h);
     dim3 grid((W + tile_w - 1) / tile_w, (H + tile_h - 1) / tile_h, V);
     if (grid.y > 65535) return fail(GMPI_ERR_UNSUPPORTED, "image height %d too large", H);
+    if (V > 65535) return fail(GMPI_ERR_UNSUPPORTED, "V=%d views exceed one launch of the direct kernel (65535); split the batch", V);
     if (options & GMPI_ALIGN_CORNERS) {
         GMPI_CUDA_OK(cudaFuncSetAttribute(mpi_bwd_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mpi_bwd_direct_kernel<true><<<grid, block, smem, st>>>(p, tile_w, tile_h);
@@ -522,7 +538,7 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
     if (encode_slab_map(&maps.t, transmittance, (uint64_t)V * N, H, W, kTileW, kTileH, 1) != 0)
         return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled (transmittance) failed");
     RenderParams p{};
-    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.z_dir = z_dir;
+    p.rgba = rgba; p.view2mpi = view2mpi; p.dhw = dhw; p.ray_dir = ray_dir; p.eye = eye; p.eye0 = eye; p.z_dir = z_dir;
     p.g_color = g_color; p.g_depth = g_depth; p.g_rgba = g_rgba; p.transmittance = const_cast<float*>(transmittance);
     p.M = M; p.V = V; p.N = N; p.Ht = Ht; p.Wt = Wt; p.H = H; p.W = W; p.options = options;
     int dev = 0, sms = 0;
@@ -608,6 +624,7 @@ struct HostCache {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
 };
 static HostCache g_host_cache[64];
+static std::mutex g_host_mutex[64];     // one call at a time per device: the staging buffers are shared state
 
 static void host_cache_release(HostCache& c) {
     for (int k = 0; k < 2; ++k) {
@@ -625,6 +642,7 @@ int gmpi_mpi_release_host_cache(void) {
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 64; ++d) {
+        std::lock_guard<std::mutex> lock(g_host_mutex[d]);
         HostCache& c = g_host_cache[d];
         if (!c.misc && !c.mpi[0] && !c.s_run) continue;
         cudaSetDevice(d);
@@ -633,6 +651,10 @@ int gmpi_mpi_release_host_cache(void) {
     cudaSetDevice(cur);
     return GMPI_OK;
 }
+
+static int host_render_locked(HostCache& c, const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                              const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags_out,
+                              int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options);
 
 int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
                              const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags_out,
@@ -646,7 +668,26 @@ int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const f
     for (int v = 0; v < V; ++v)
         if (view2mpi[v] < 0 || view2mpi[v] >= M) return fail(GMPI_ERR_INVALID_ARGUMENT, "view2mpi[%d]=%d out of range", v, view2mpi[v]);
     GMPI_CUDA_OK(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_host_mutex[device]);
     HostCache& c = g_host_cache[device];
+    rc = host_render_locked(c, rgba, view2mpi, dhw, ray_dir, eye, z_dir, color, depth, flags_out, M, V, N, Ht, Wt, H, W, options);
+    if (rc != GMPI_OK) {
+        // An error may have left asynchronous copies reading the caller's host buffers or rendering from the staging slots:
+        // drain both streams before returning so that the caller may free its buffers and the next call starts clean.
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        if (c.s_run) cudaStreamSynchronize(c.s_run);
+        if (c.s_copy) cudaStreamSynchronize(c.s_copy);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof(keep));
+    }
+    return rc;
+}
+
+static int host_render_locked(HostCache& c, const float* rgba, const int32_t* view2mpi, const float* dhw, const float* ray_dir,
+                              const float* eye, const float* z_dir, float* color, float* depth, uint32_t* flags_out,
+                              int M, int V, int N, int Ht, int Wt, int H, int W, uint32_t options) {
+    int rc = GMPI_OK;
     const size_t tex = (size_t)Ht * Wt, img = (size_t)H * W;
     const size_t mpi_bytes = sizeof(float) * (size_t)N * 4 * tex;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -698,10 +739,10 @@ int gmpi_mpi_render_fwd_host(const float* rgba, const int32_t* view2mpi, const f
         GMPI_CUDA_OK(cudaMemcpyAsync(c.mpi[slot], rgba + (size_t)m * N * 4 * tex, mpi_bytes, cudaMemcpyHostToDevice, s_copy));
         GMPI_CUDA_OK(cudaEventRecord(c.ev_in[slot], s_copy));
         GMPI_CUDA_OK(cudaStreamWaitEvent(s_run, c.ev_in[slot], 0));
-        // mpi.py:70 compares every distance with view 0's eye; here: with the first view of each MPI's launch
-        rc = gmpi_mpi_render_fwd(c.mpi[slot], d_v2m, d_dhw + (size_t)m * N * 3, d_ray + (size_t)v0 * 3 * img, d_eye + (size_t)v0 * 3,
-                                 d_z + (size_t)v0 * 3, d_color + (size_t)v0 * 3 * img, d_depth + (size_t)v0 * img, d_flags, 1, v1 - v0, N,
-                                 Ht, Wt, H, W, options, s_run);
+        // mpi.py:70 compares every plane distance with the eye of the CALL's view 0 (d_eye), not of this launch's first view
+        rc = render_fwd_impl(c.mpi[slot], d_v2m, d_dhw + (size_t)m * N * 3, d_ray + (size_t)v0 * 3 * img, d_eye + (size_t)v0 * 3, d_eye,
+                             d_z + (size_t)v0 * 3, d_color + (size_t)v0 * 3 * img, d_depth + (size_t)v0 * img, d_flags, nullptr, 0, 0,
+                             nullptr, 1, v1 - v0, N, Ht, Wt, H, W, options, s_run);
         if (rc) return rc;
         GMPI_CUDA_OK(cudaEventRecord(c.ev_free[slot], s_run));
         used[slot] = 1;

@@ -55,11 +55,20 @@ def all_gather_frames(frames: torch.Tensor, counts: List[int] = None, group=None
 class FrameGather:
     """All-gather of rendered frames fused into the render kernel (the one collective of the path).
 
-    Every rank owns a symmetric-memory buffer [world * frames_per_rank, 4, H, W] that all peers map over NVLink
+    Every rank owns symmetric-memory buffers [world * frames_per_rank, 4, H, W] that all peers map over NVLink
     (torch.distributed._symmetric_memory).  `render()` launches the forward kernel with the peers' buffer pointers: the
     epilogue stores each finished pixel into frame slot rank * frames_per_rank + v of EVERY rank's buffer, so the gather
     overlaps the render tile by tile (posted NVLink writes) instead of following it as a separate ncclAllGather;
     `finish()` is the device-side barrier that makes the remote stores visible.  `frames` is then the gathered tensor.
+
+    Ordering (write-after-read across iterations).  The buffers are DOUBLE-BUFFERED: step k writes buffer k % 2.  A peer
+    may start step k+2 (which overwrites buffer k % 2 on every rank) only after it passed barrier k+1, and barrier k+1
+    completes on a rank only when that rank's stream has reached its own `finish()` of step k+1.  So every kernel that reads
+    `frames` of step k is safe provided it was enqueued ON THE RENDER STREAM (or on a stream the render stream waits on)
+    before the next `finish()` -- the natural program order render, finish, consume, render, finish, ...  A consumer on an
+    unrelated stream must be joined to the render stream first.  (Round 1 had one buffer and only the trailing barrier: a fast
+    rank's step k+1 could overwrite frames a slow rank was still reading; tests/test_gpu_multi.py renders different data
+    per step with a reader in flight to cover this.)
     """
 
     def __init__(self, frames_per_rank: int, H: int, W: int, device, group=None):
@@ -67,11 +76,22 @@ class FrameGather:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.frames_per_rank, self.H, self.W = frames_per_rank, H, W
-        self.frames = symm_mem.empty((self.world * frames_per_rank, 4, H, W), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.frames, self.group)
-        ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        assert len(ptrs) == self.world
-        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)   # device array of float* (one per rank)
+        self._bufs, self._handles, self._peer_ptrs = [], [], []
+        for _ in range(2):
+            buf = symm_mem.empty((self.world * frames_per_rank, 4, H, W), dtype=torch.float32, device=device)
+            handle = symm_mem.rendezvous(buf, self.group)
+            ptrs = [int(p) for p in handle.buffer_ptrs]
+            assert len(ptrs) == self.world
+            self._bufs.append(buf)
+            self._handles.append(handle)
+            self._peer_ptrs.append(torch.tensor(ptrs, dtype=torch.int64, device=device))   # device array of float* (one per rank)
+        self._next, self._done = 0, None
+
+    @property
+    def frames(self) -> torch.Tensor:
+        """The gathered frames of the most recently finished step ([world * frames_per_rank, 4, H, W])."""
+        assert self._done is not None, "no finished step yet: call render() and finish() first"
+        return self._bufs[self._done]
 
     def render(self, rgba, dhw, view2mpi, ray_dir, eye, z_dir, flags, *, align_corners=True, check_last_plane=False,
                color_minus1_1=False):
@@ -85,9 +105,11 @@ class FrameGather:
         with torch.cuda.device(rgba.device):
             _lib.check(lib.gmpi_mpi_render_fwd_gather(
                 rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
-                self.peer_ptrs.data_ptr(), self.world, self.rank * self.frames_per_rank, flags.data_ptr(),
+                self._peer_ptrs[self._next].data_ptr(), self.world, self.rank * self.frames_per_rank, flags.data_ptr(),
                 M, V, N, Ht, Wt, self.H, self.W, options, torch.cuda.current_stream(rgba.device).cuda_stream))
 
     def finish(self):
         """Barrier across ranks on the current stream: after it, every rank's `frames` holds all ranks' frames."""
-        self.handle.barrier(channel=0)
+        self._handles[self._next].barrier(channel=0)
+        self._done = self._next
+        self._next ^= 1

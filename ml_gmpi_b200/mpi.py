@@ -6,6 +6,8 @@ mpi.py:65,148).
 
 No CPU path: tensors must live on a CUDA device, otherwise this raises.
 """
+import ctypes
+import warnings
 from typing import List, Optional, Union
 
 import numpy as np
@@ -59,7 +61,8 @@ class _RenderFn(torch.autograd.Function):
         return color, depth
 
     @staticmethod
-    def backward(ctx, g_color, g_depth):
+    @torch.autograd.function.once_differentiable     # raw kernels: a double backward (create_graph=True) must raise, not
+    def backward(ctx, g_color, g_depth):             # silently treat g_rgba as constant (the reference's R1 only differentiates D)
         rgba, dhw, view2mpi, ray_dir, eye, z_dir, trans = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
             return (None,) * 8
@@ -88,6 +91,24 @@ class _RenderFn(torch.autograd.Function):
         return g_rgba, None, None, None, None, None, None, None
 
 
+_warned_direct = set()
+
+
+def _warn_if_direct(rgba, V, H, W):
+    """Surface the direct-kernel performance cliff (several times slower than the TMA-staged kernels) once per shape."""
+    M, N, _, Ht, Wt = rgba.shape
+    key = (V, N, Ht, Wt, H, W, rgba.data_ptr() & 15)
+    if key in _warned_direct:
+        return
+    _warned_direct.add(key)
+    why = ctypes.c_uint32(0)
+    if _lib.load().gmpi_mpi_render_fwd_plan(V, N, Ht, Wt, H, W, rgba.data_ptr(), ctypes.byref(why)) == _lib.PLAN_DIRECT \
+            and (why.value & ~2 or V * N * H * W >= 1 << 26):      # "few tiles" only matters when the problem is not tiny
+        reasons = "; ".join(t for b, t in _lib.WHY.items() if why.value & b)
+        warnings.warn(f"ml_gmpi_b200: rendering V={V} N={N} tex={Ht}x{Wt} img={H}x{W} with the direct (one thread per pixel) "
+                      f"kernels, several times slower than the TMA-staged path: {reasons}", RuntimeWarning, stacklevel=3)
+
+
 def render_views(rgba, dhw, view2mpi, ray_dir, eye, z_dir, *, align_corners=True, check_last_plane=False,
                  color_minus1_1=False, flags: Optional[torch.Tensor] = None):
     """Functional form on packed tensors (no list handling, no host sync).
@@ -97,6 +118,7 @@ def render_views(rgba, dhw, view2mpi, ray_dir, eye, z_dir, *, align_corners=True
         raise RuntimeError("ml_gmpi_b200 renders on CUDA devices only (no CPU fallback); got a CPU tensor")
     if flags is None:
         flags = torch.zeros(1, dtype=torch.int32, device=rgba.device)
+    _warn_if_direct(rgba, ray_dir.shape[0], ray_dir.shape[2], ray_dir.shape[3])
     options = (_lib.OPT_ALIGN_CORNERS if align_corners else 0) | (_lib.OPT_CHECK_LAST_PLANE if check_last_plane else 0) \
         | (_lib.OPT_COLOR_MINUS1_1 if color_minus1_1 else 0)
     return _RenderFn.apply(_as_f32c(rgba), _as_f32c(dhw), view2mpi, _as_f32c(ray_dir), _as_f32c(eye), _as_f32c(z_dir),

@@ -283,66 +283,115 @@ void gmpi_oracle_forward_over(const float* rgba, const int32_t* view2mpi, const 
  * then grid_sampler_2d_backward scatters each through the four bilinear weights.
  * g_depth may be NULL.  g_rgba must be zero-initialised by the caller; views accumulate.
  */
+typedef struct {
+    const float *rgba, *dhw, *ray_dir, *eye, *z_dir, *g_color, *g_depth;
+    float* g_rgba;
+    int m, v, N, Ht, Wt, H, W, align_corners, row0, row1, atomic;
+} bwd_job_t;
+
+/* g += x.  With several row bands in flight two threads may hit the same texel (bilinear footprints of neighbouring rows
+ * overlap): compare-and-swap on the bit pattern.  The sum is then order-dependent at the last-ulp level only. */
+static inline void grad_add(float* g, float x, int atomic) {
+    if (!atomic) { *g += x; return; }
+    uint32_t* u = (uint32_t*)g;
+    uint32_t old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+    do {
+        float f;
+        memcpy(&f, &old, 4);
+        f += x;
+        memcpy(&neu, &f, 4);
+    } while (!__atomic_compare_exchange_n(u, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+
+static void* bwd_rows(void* arg) {
+    bwd_job_t* j = (bwd_job_t*)arg;
+    const int N = j->N, Ht = j->Ht, Wt = j->Wt, H = j->H, W = j->W, v = j->v, m = j->m;
+    const size_t tex = (size_t)Ht * Wt, img = (size_t)H * W;
+    (void)H;
+    float* sa = (float*)malloc(sizeof(float) * N * 6);
+    float *A = sa, *P = sa + N, *Q = sa + 2 * N, *SUF = sa + 3 * N, *S = sa + 4 * N, *GA = sa + 5 * N;
+    taps_t* tp = (taps_t*)malloc(sizeof(taps_t) * N);
+    const float* e = j->eye + 3 * v;
+    const float* zd = j->z_dir + 3 * v;
+    for (int py = j->row0; py < j->row1; ++py)
+        for (int px = 0; px < W; ++px) {
+            const size_t p = (size_t)py * W + px;
+            const float rx = j->ray_dir[((size_t)v * 3 + 0) * img + p];
+            const float ry = j->ray_dir[((size_t)v * 3 + 1) * img + p];
+            const float rz = j->ray_dir[((size_t)v * 3 + 2) * img + p];
+            const float dist2depth = rx * zd[0] + ry * zd[1] + rz * zd[2];
+            const float G0 = j->g_color[((size_t)v * 3 + 0) * img + p];
+            const float G1 = j->g_color[((size_t)v * 3 + 1) * img + p];
+            const float G2 = j->g_color[((size_t)v * 3 + 2) * img + p];
+            const float Gd = j->g_depth ? j->g_depth[(size_t)v * img + p] : 0.0f;
+            float T = 1.0f;
+            for (int i = 0; i < N; ++i) {
+                const float* pd = j->dhw + ((size_t)m * N + i) * 3;
+                coord_t c = plane_coord(pd[0], pd[1], pd[2], e, rx, ry, rz, Ht, Wt, j->align_corners);
+                tp[i] = bilinear_taps(c.ix, c.iy, Ht, Wt);
+                const float* base = j->rgba + ((size_t)m * N + i) * 4 * tex;
+                float r = tap_sum(base, &tp[i], Wt), g = tap_sum(base + tex, &tp[i], Wt);
+                float b = tap_sum(base + 2 * tex, &tp[i], Wt), a = tap_sum(base + 3 * tex, &tp[i], Wt);
+                float dpt = 1.0f / (1.0f / (c.scale * dist2depth));
+                A[i] = a; P[i] = T; S[i] = (1.0f - a) + 1e-10f;
+                Q[i] = G0 * r + G1 * g + G2 * b + Gd * dpt;
+                T = T * S[i];
+            }
+            float suf = 0.0f;   /* reversed cumsum, back to front */
+            for (int i = N - 1; i >= 0; --i) {
+                SUF[i] = suf;
+                suf += A[i] * Q[i] * P[i];
+            }
+            for (int i = 0; i < N; ++i) GA[i] = P[i] * Q[i] - SUF[i] / S[i];
+            for (int i = 0; i < N; ++i) {
+                float* gb = j->g_rgba + ((size_t)m * N + i) * 4 * tex;
+                const float wgt = A[i] * P[i];
+                const float gch[4] = {G0 * wgt, G1 * wgt, G2 * wgt, GA[i]};
+                const taps_t* t = &tp[i];
+                for (int ch = 0; ch < 4; ++ch) {
+                    float* gc = gb + (size_t)ch * tex;
+                    if (t->ok[0]) grad_add(gc + (size_t)t->y0 * Wt + t->x0, gch[ch] * t->w[0], j->atomic);
+                    if (t->ok[1]) grad_add(gc + (size_t)t->y0 * Wt + t->x0 + 1, gch[ch] * t->w[1], j->atomic);
+                    if (t->ok[2]) grad_add(gc + (size_t)(t->y0 + 1) * Wt + t->x0, gch[ch] * t->w[2], j->atomic);
+                    if (t->ok[3]) grad_add(gc + (size_t)(t->y0 + 1) * Wt + t->x0 + 1, gch[ch] * t->w[3], j->atomic);
+                }
+            }
+        }
+    free(sa);
+    free(tp);
+    return NULL;
+}
+
+/* Row bands of each view on `nthreads` pthreads (views one after another).  nthreads == 1 is the plain sequential sum. */
+void gmpi_oracle_backward_mt(const float* rgba, const int32_t* view2mpi, const float* dhw,
+                             const float* ray_dir, const float* eye, const float* z_dir,
+                             const float* g_color, const float* g_depth, float* g_rgba, int M, int V,
+                             int N, int Ht, int Wt, int H, int W, int align_corners, int nthreads) {
+    (void)M;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > H) nthreads = H;
+    if (nthreads > 256) nthreads = 256;
+    for (int v = 0; v < V; ++v) {
+        bwd_job_t jobs[256];
+        pthread_t th[256];
+        for (int t = 0; t < nthreads; ++t) {
+            bwd_job_t jb = {rgba, dhw, ray_dir, eye, z_dir, g_color, g_depth, g_rgba, view2mpi[v], v, N, Ht, Wt, H, W,
+                            align_corners, (int)((long)H * t / nthreads), (int)((long)H * (t + 1) / nthreads), nthreads > 1};
+            jobs[t] = jb;
+            if (nthreads == 1) bwd_rows(&jobs[t]);
+            else pthread_create(&th[t], NULL, bwd_rows, &jobs[t]);
+        }
+        if (nthreads > 1)
+            for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    }
+}
+
 void gmpi_oracle_backward(const float* rgba, const int32_t* view2mpi, const float* dhw,
                           const float* ray_dir, const float* eye, const float* z_dir,
                           const float* g_color, const float* g_depth, float* g_rgba, int M, int V,
                           int N, int Ht, int Wt, int H, int W, int align_corners) {
-    const size_t tex = (size_t)Ht * Wt, img = (size_t)H * W;
-    (void)M;
-    float* sa = (float*)malloc(sizeof(float) * N * 6);
-    float *A = sa, *P = sa + N, *Q = sa + 2 * N, *SUF = sa + 3 * N, *S = sa + 4 * N, *GA = sa + 5 * N;
-    taps_t* tp = (taps_t*)malloc(sizeof(taps_t) * N);
-    for (int v = 0; v < V; ++v) {
-        const int m = view2mpi[v];
-        const float* e = eye + 3 * v;
-        const float* zd = z_dir + 3 * v;
-        for (int py = 0; py < H; ++py)
-            for (int px = 0; px < W; ++px) {
-                const size_t p = (size_t)py * W + px;
-                const float rx = ray_dir[((size_t)v * 3 + 0) * img + p];
-                const float ry = ray_dir[((size_t)v * 3 + 1) * img + p];
-                const float rz = ray_dir[((size_t)v * 3 + 2) * img + p];
-                const float dist2depth = rx * zd[0] + ry * zd[1] + rz * zd[2];
-                const float G0 = g_color[((size_t)v * 3 + 0) * img + p];
-                const float G1 = g_color[((size_t)v * 3 + 1) * img + p];
-                const float G2 = g_color[((size_t)v * 3 + 2) * img + p];
-                const float Gd = g_depth ? g_depth[(size_t)v * img + p] : 0.0f;
-                float T = 1.0f;
-                for (int i = 0; i < N; ++i) {
-                    const float* pd = dhw + ((size_t)m * N + i) * 3;
-                    coord_t c = plane_coord(pd[0], pd[1], pd[2], e, rx, ry, rz, Ht, Wt, align_corners);
-                    tp[i] = bilinear_taps(c.ix, c.iy, Ht, Wt);
-                    const float* base = rgba + ((size_t)m * N + i) * 4 * tex;
-                    float r = tap_sum(base, &tp[i], Wt), g = tap_sum(base + tex, &tp[i], Wt);
-                    float b = tap_sum(base + 2 * tex, &tp[i], Wt), a = tap_sum(base + 3 * tex, &tp[i], Wt);
-                    float dpt = 1.0f / (1.0f / (c.scale * dist2depth));
-                    A[i] = a; P[i] = T; S[i] = (1.0f - a) + 1e-10f;
-                    Q[i] = G0 * r + G1 * g + G2 * b + Gd * dpt;
-                    T = T * S[i];
-                }
-                float suf = 0.0f;   /* reversed cumsum, back to front */
-                for (int i = N - 1; i >= 0; --i) {
-                    SUF[i] = suf;
-                    suf += A[i] * Q[i] * P[i];
-                }
-                for (int i = 0; i < N; ++i) GA[i] = P[i] * Q[i] - SUF[i] / S[i];
-                for (int i = 0; i < N; ++i) {
-                    float* gb = g_rgba + ((size_t)m * N + i) * 4 * tex;
-                    const float wgt = A[i] * P[i];
-                    const float gch[4] = {G0 * wgt, G1 * wgt, G2 * wgt, GA[i]};
-                    const taps_t* t = &tp[i];
-                    for (int ch = 0; ch < 4; ++ch) {
-                        float* gc = gb + (size_t)ch * tex;
-                        if (t->ok[0]) gc[(size_t)t->y0 * Wt + t->x0] += gch[ch] * t->w[0];
-                        if (t->ok[1]) gc[(size_t)t->y0 * Wt + t->x0 + 1] += gch[ch] * t->w[1];
-                        if (t->ok[2]) gc[(size_t)(t->y0 + 1) * Wt + t->x0] += gch[ch] * t->w[2];
-                        if (t->ok[3]) gc[(size_t)(t->y0 + 1) * Wt + t->x0 + 1] += gch[ch] * t->w[3];
-                    }
-                }
-            }
-    }
-    free(sa);
-    free(tp);
+    gmpi_oracle_backward_mt(rgba, view2mpi, dhw, ray_dir, eye, z_dir, g_color, g_depth, g_rgba, M, V, N, Ht, Wt, H, W,
+                            align_corners, 1);
 }
 
 /* Texel coordinates only (for bit-exactness tests of the coordinate stage): out [V,N,2,H,W]. */

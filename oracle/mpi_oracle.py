@@ -41,8 +41,8 @@ def lib():
         _lib.gmpi_oracle_forward_mt.argtypes = [fp, ip, fp, fp, fp, fp, fp, fp] + [i] * 10
         _lib.gmpi_oracle_forward_over.restype = None
         _lib.gmpi_oracle_forward_over.argtypes = [fp, ip, fp, fp, fp, fp, fp, fp] + [i] * 8
-        _lib.gmpi_oracle_backward.restype = None
-        _lib.gmpi_oracle_backward.argtypes = [fp, ip, fp, fp, fp, fp, fp, fp, fp] + [i] * 8
+        _lib.gmpi_oracle_backward_mt.restype = None
+        _lib.gmpi_oracle_backward_mt.argtypes = [fp, ip, fp, fp, fp, fp, fp, fp, fp] + [i] * 9
         _lib.gmpi_oracle_coords.restype = None
         _lib.gmpi_oracle_coords.argtypes = [ip, fp, fp, fp, fp] + [i] * 7
         _lib.gmpi_oracle_check_range.restype = ctypes.c_uint32
@@ -95,8 +95,9 @@ def forward_over(rgba, view2mpi, dhw, ray_dir, eye, z_dir, align_corners=True):
     return color, depth
 
 
-def backward(rgba, view2mpi, dhw, ray_dir, eye, z_dir, g_color, g_depth=None, align_corners=True):
-    """-> g_rgba [M,N,4,Ht,Wt]"""
+def backward(rgba, view2mpi, dhw, ray_dir, eye, z_dir, g_color, g_depth=None, align_corners=True, nthreads=1):
+    """-> g_rgba [M,N,4,Ht,Wt].  nthreads > 1 splits each view's rows over pthreads (atomic float adds: the summation
+    order, hence the last ulp, then varies from run to run; nthreads == 1 is the sequential reference sum)."""
     M, N, Ht, Wt, V, H, W = _shapes(rgba, ray_dir)
     rgba, p_rgba = _f(rgba); v2m, p_v2m = _i(view2mpi); dhw, p_dhw = _f(dhw)
     ray_dir, p_ray = _f(ray_dir); eye, p_eye = _f(eye); z_dir, p_z = _f(z_dir)
@@ -106,10 +107,10 @@ def backward(rgba, view2mpi, dhw, ray_dir, eye, z_dir, g_color, g_depth=None, al
     else:
         g_depth, p_gd = _f(g_depth)
     g_rgba = np.zeros((M, N, 4, Ht, Wt), np.float32)
-    lib().gmpi_oracle_backward(
+    lib().gmpi_oracle_backward_mt(
         p_rgba, p_v2m, p_dhw, p_ray, p_eye, p_z, p_gc, p_gd,
         g_rgba.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
-        M, V, N, Ht, Wt, H, W, int(bool(align_corners)))
+        M, V, N, Ht, Wt, H, W, int(bool(align_corners)), int(nthreads))
     return g_rgba
 
 

@@ -91,3 +91,12 @@ def test_pack_views_is_mpi_major():
     v2m, ray, eye, z = g.MPI.pack_views(rays, eyes, eyes, torch.device("cpu"))
     assert v2m.tolist() == [0, 0, 1, 2, 2, 2] and v2m.dtype == torch.int32
     assert ray.shape == (6, 3, 4, 4) and float(ray[2].min()) == 1.0
+
+
+def test_plan_query_needs_no_gpu(lib):
+    why = ctypes.c_uint32(0)
+    assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1024, 1024, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_STAGED and why.value == 0
+    assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1022, 1022, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 1
+    assert lib.gmpi_mpi_render_fwd_plan(1, 16, 64, 64, 48, 48, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 2
+    assert lib.gmpi_mpi_render_fwd_plan(4, 600, 1024, 1024, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 4
+    assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1024, 1024, 1024, 1024, 8, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 8

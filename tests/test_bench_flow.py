@@ -1,0 +1,67 @@
+"""bench.py's control flow for world_size 1 and 2, on CPU: gloo process group, the renderer replaced by bench.FakeBackend
+(`--fake`).  Round 1 shipped a bench that crashed at N>1 because the default command line had never run there (the e2e
+check compared against buffers the fused-gather mode never writes); this test runs exactly that command line shape."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _run(world, extra_env=None, extra_args=()):
+    port = _free_port()
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        env.update(extra_env or {})
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "bench.py"), "--fake", "--gpus", str(world), "--steps", "3",
+                                       "--warmup", "1", *extra_args], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    lines = [l for l in outs[0][0].splitlines() if l.startswith("{")]
+    assert len(lines) == 1, outs[0]
+    assert all(not [l for l in so.splitlines() if l.startswith("{")] for so, _ in outs[1:])     # only rank 0 prints
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("world,no_symm", [(1, False), (2, False), (2, True)])
+def test_default_command_line_runs_every_leg(world, no_symm):
+    line = _run(world, {"GMPI_FAKE_NO_SYMM": "1"} if no_symm else None)
+    assert line["n_gpus"] == world and line["steps"] == 3 and line["warmup"] == 3 and line["value"] > 0
+    assert line["scaling"] == "weak" and line["higher_is_better"] is True and line["gpu_launches"] == 3
+    for key in ("metric", "unit", "ms_per_step", "dtype", "data", "config", "roofline", "e2e", "train_step", "configs"):
+        assert line.get(key) is not None, key
+    assert line["e2e"]["matches_device_resident_run"] and line["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(line["configs"]) == {"C2_ffhq256_fwd", "C4_video_512", "C5_train_512"}
+    assert line["configs"]["C4_video_512"]["scaling"] == "strong"
+    par = line["config"]["parallelism"]
+    if world == 1:
+        assert "none" in par
+    elif no_symm:
+        assert "ncclAllGather" in par
+    else:
+        assert "fused" in par
+
+
+def test_reference_arm_only_rank0_prints_and_others_exit_zero():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_usable_cores_respects_affinity():
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= len(os.sched_getaffinity(0))

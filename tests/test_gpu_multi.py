@@ -34,7 +34,32 @@ def _worker(rank, world, port, q):
             fg.render(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, flags, color_minus1_1=True)
             fg.finish()
         torch.cuda.synchronize(dev)
-        q.put((rank, bool(torch.equal(fg.frames, ref)), float((fg.frames - ref).abs().max()), int(flags.item())))
+        ok = bool(torch.equal(fg.frames, ref))
+        maxdiff = float((fg.frames - ref).abs().max())
+        # write-after-read across iterations: DIFFERENT data every step, ranks deliberately skewed, and a reader
+        # of step k's frames still in flight on the render stream while the peers already run step k+1
+        cases = [case, synth.make_case(n_planes=N, tex=R, img=R, n_mpi=B, seed=500 + rank, device=dev)]
+        refs = []
+        for c in cases:
+            cc, dd = g.render_views(c.rgba, c.dhw, c.view2mpi, c.ray_dir, c.eye, c.z_dir, color_minus1_1=True)
+            refs.append(gdist.all_gather_frames(gdist.pack_frames(cc, dd)))
+        snaps = []
+        for k in range(8):
+            c = cases[k % 2]
+            if (k + rank) % 2:
+                torch.cuda._sleep(20_000_000)                                        # ~10 ms of skew on alternating ranks
+            fg.render(c.rgba, c.dhw, c.view2mpi, c.ray_dir, c.eye, c.z_dir, flags, color_minus1_1=True)
+            fg.finish()
+            snap = fg.frames.clone()                                                 # the in-flight reader
+            for _ in range(4):
+                snap = snap + 0.0
+            snaps.append(snap)
+        torch.cuda.synchronize(dev)
+        for k, snap in enumerate(snaps):
+            if not torch.equal(snap, refs[k % 2]):
+                ok = False
+                maxdiff = max(maxdiff, float((snap - refs[k % 2]).abs().max()))
+        q.put((rank, ok, maxdiff, int(flags.item())))
     finally:
         dist.destroy_process_group()
 

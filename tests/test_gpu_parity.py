@@ -240,10 +240,9 @@ def test_zero_alpha_renders_nothing_and_linearity_in_rgb(fwd_variant):
     assert torch.equal(da, db)                                              # depth ignores rgb
 
 
-def test_full_size_backward_c3_view_vs_oracle(fwd_variant):
-    """BASELINE configs[2] shape (96 planes, 1024^2) gradient on a 96x1024 strip vs the oracle is too slow for
-    the CPU; use 96 planes at 128^2 with the production alpha==1 last plane instead, plus gradient accumulation
-    over views sharing one MPI."""
+def test_backward_96_planes_small_image_shared_mpi_vs_oracle(fwd_variant):
+    """96 planes at 128^2 with the production alpha==1 last plane, two views accumulating into one MPI's gradient (the
+    full-size C3/C5/C4 shapes are further down: test_full_size_*)."""
     d = dev()
     from ml_gmpi_b200 import synth
     case = synth.make_case(n_planes=96, tex=128, img=128, n_mpi=1, views_per_mpi=2, seed=5, device=d, last_alpha_one=True)
@@ -362,3 +361,107 @@ def test_backward_staged_multi_tile_batch_vs_oracle(fwd_variant):
     (c2 * gc).sum().backward()
     ref2 = mpi_oracle.backward(n(base), n(case.view2mpi), n(case.dhw), n(case.ray_dir), n(case.eye), n(case.z_dir), n(gc), None)
     assert rel_err(n(rgba2.grad), ref2) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs at their REAL sizes (round-1 VERDICT: the staged backward had never been compared with the oracle
+# at its operating point -- 1024^2 textures, 35x16 tiles per view, a saved-transmittance tensor map over V*N slabs, tap
+# hand-over across tile edges).  The oracle's rows run on pthreads (atomic float adds, last-ulp order dependence only).
+# ------------------------------------------------------------------------------------------------
+import os as _os
+_NT = max(1, min(64, (_os.cpu_count() or 8)))
+
+
+def _grad_check(case, with_depth, minus1_1=False, seed=3):
+    d = case.rgba.device
+    rgba = case.rgba.clone().requires_grad_(True)
+    color, depth = g.render_views(rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, color_minus1_1=minus1_1)
+    gen = torch.Generator().manual_seed(seed)
+    gc = torch.randn(color.shape, generator=gen).to(d)
+    gdp = torch.randn(depth.shape, generator=gen).to(d) if with_depth else None
+    loss = (color * gc).sum()
+    if with_depth:
+        loss = loss + (depth * gdp).sum()
+    loss.backward()
+    n = lambda t: t.detach().cpu().numpy()
+    ref = mpi_oracle.backward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(case.ray_dir), n(case.eye), n(case.z_dir),
+                              (2.0 if minus1_1 else 1.0) * n(gc), n(gdp) if with_depth else None, nthreads=_NT)
+    ours = n(rgba.grad)
+    del rgba, color, depth, loss
+    return rel_err(ours, ref)
+
+
+def test_full_size_backward_c3_one_view_96x1024_vs_oracle(fwd_variant):
+    """BASELINE configs[2] (FFHQ1024 forward+backward): one 96-plane 1024^2 view, production alpha==1 last plane, colour and
+    depth upstream gradients.  (gmpi/core/mpi.py:411-436 autograd; train.py:733-740.)"""
+    from ml_gmpi_b200 import synth
+    case = synth.make_case(n_planes=96, tex=1024, img=1024, n_mpi=1, seed=1234, device=dev(), last_alpha_one=True)
+    assert _grad_check(case, with_depth=True) <= EXPECT
+
+
+def test_full_size_backward_c5_batch4_96x512_vs_oracle(fwd_variant):
+    """BASELINE configs[4] per-GPU shape: M = V = 4, 96 planes, 512^2, alpha==1 last plane, colour-only upstream gradient w.r.t.
+    2c-1 (what train.py:740,779 backpropagates; the depth output is discarded there)."""
+    from ml_gmpi_b200 import synth
+    case = synth.make_case(n_planes=96, tex=512, img=512, n_mpi=4, seed=99, device=dev(), last_alpha_one=True)
+    assert _grad_check(case, with_depth=False, minus1_1=True) <= EXPECT
+
+
+def test_full_size_backward_four_views_share_one_mpi_512_vs_oracle(fwd_variant):
+    """Gradient accumulation over 4 views of ONE MPI at 512^2 (the expand of train.py:733-738, train_helpers.py:181-186)."""
+    from ml_gmpi_b200 import synth
+    case = synth.make_case(n_planes=48, tex=512, img=512, n_mpi=1, views_per_mpi=4, seed=21, device=dev(), last_alpha_one=True)
+    assert _grad_check(case, with_depth=True) <= EXPECT
+
+
+def test_full_size_forward_c4_video_every_view_vs_oracle(fwd_variant):
+    """BASELINE configs[3] shape: ONE 96-plane 512^2 MPI, 15 views (one rank's share of the 120) spread over the whole
+    yaw = linspace(0.5, -0.5, 120) sweep, pitch 0 (render_video.py:95-107); every view against the oracle."""
+    from ml_gmpi_b200 import synth
+    yaws = np.linspace(0.5, -0.5, 120).astype(np.float32)[::8]
+    assert len(yaws) == 15
+    case = synth.make_case(n_planes=96, tex=512, img=512, n_mpi=1, views_per_mpi=15, seed=1234, device=dev(), yaws=yaws,
+                           pitches=np.zeros(15, np.float32))
+    color, depth = g.render_views(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, check_last_plane=True)
+    n = lambda t: t.cpu().numpy()
+    rc, rd, _ = mpi_oracle.forward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(case.ray_dir), n(case.eye), n(case.z_dir),
+                                   nthreads=_NT)
+    for v in range(15):
+        assert rel_err(n(color[v]), rc[v]) <= EXPECT and rel_err(n(depth[v]), rd[v]) <= EXPECT, v
+
+
+def test_non_projective_rays_outside_the_corner_box_still_render(fwd_variant):
+    """the producer's "nothing under the tile" (mode 1) comes from the four corner rays only.  Rays that are not a
+    pinhole camera's can have all four tile corners miss the texture while interior pixels hit it: those pixels must still
+    be rendered (and get gradient), exactly as the direct kernel and the oracle do."""
+    from ml_gmpi_b200 import synth
+    d = dev()
+    case = synth.make_case(n_planes=6, tex=64, img=128, n_mpi=1, views_per_mpi=2, seed=9, device=d)   # 2x5 tiles per view
+    ray = case.ray_dir.clone()
+    # push the corner pixels of every 64x30 tile far outside the planes, keep the interior as it is
+    for ty in range(0, 128, 30):
+        for tx in range(0, 128, 64):
+            for (cy, cx) in ((ty, tx), (ty, min(tx + 63, 127)), (min(ty + 29, 127), tx), (min(ty + 29, 127), min(tx + 63, 127))):
+                ray[:, 0, cy, cx] = 5.0
+    rgba = case.rgba.clone().requires_grad_(True)
+    color, depth = g.render_views(rgba, case.dhw, case.view2mpi, ray, case.eye, case.z_dir)
+    gen = torch.Generator().manual_seed(2)
+    gc = torch.randn(color.shape, generator=gen).to(d)
+    (color * gc).sum().backward()
+    n = lambda t: t.detach().cpu().numpy()
+    rc, rd, _ = mpi_oracle.forward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(ray), n(case.eye), n(case.z_dir))
+    assert float(np.abs(rc).max()) > 0.1                       # the interior really renders something
+    assert rel_err(n(color), rc) <= EXPECT and rel_err(n(depth), rd) <= EXPECT
+    ref = mpi_oracle.backward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(ray), n(case.eye), n(case.z_dir), n(gc), None)
+    assert rel_err(n(rgba.grad), ref) <= EXPECT
+
+
+def test_plan_query_names_the_direct_kernel_cliffs():
+    """The direct-kernel fallbacks are visible through gmpi_mpi_render_fwd_plan instead of only in a profile."""
+    import ctypes
+    lib = _lib.load()
+    why = ctypes.c_uint32(0)
+    assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1024, 1024, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_STAGED and why.value == 0
+    assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1022, 1022, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 1
+    assert lib.gmpi_mpi_render_fwd_plan(1, 16, 64, 64, 48, 48, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 2
+    assert lib.gmpi_mpi_render_fwd_plan(4, 600, 1024, 1024, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 4
