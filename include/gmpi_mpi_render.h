@@ -58,6 +58,8 @@ extern "C" {
 #define GMPI_CHECK_LAST_PLANE 2u       /* assert_not_out_of_last_plane, mpi.py:317              */
 #define GMPI_COLOR_MINUS1_1 4u         /* fuse "2*color-1" of mpi_renderer.py:467 into the store */
 #define GMPI_ZERO_GRAD 8u              /* bwd: zero g_rgba on the stream before accumulating    */
+#define GMPI_U8_ROUND_HALF_UP 16u       /* uint8 epilogue: clamp, x*255+0.5 (torchvision save_image, fid_evaluation.py:125-130)
+                                          instead of numpy's truncating astype (render_video.py:119-126) */
 
 int gmpi_abi_version(void);
 const char* gmpi_last_error(void);
@@ -136,6 +138,78 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
                               uint32_t options, void* stream);
 
 /*
+ * Descriptor form of the render calls: every optional input/output of the path in one struct, so that the variants below
+ * compose (factored MPI x in-kernel rays x video epilogue x fused all-gather x training).  Zero-initialise it, set
+ * struct_bytes = sizeof(gmpi_render_desc) and fill what applies; every pointer is DEVICE memory for gmpi_mpi_render_fwd_ex /
+ * gmpi_mpi_render_bwd_ex and HOST memory for gmpi_mpi_render_host_ex.
+ *
+ *   MPI, one of
+ *     rgba   [M,N,4,Ht,Wt]                       the expanded stack MPI.forward receives (mpi.py:309)
+ *     rgb    [M,3,Ht,Wt] + alpha [M,N,1,Ht,Wt]   the generator's FACTORED output: one colour image shared by all planes and one
+ *            (+ bg_rgb [M,3,Ht,Wt], optional)    alpha per plane, before the reference expands and concatenates them
+ *                                                (networks_cond_on_pos_enc.py:950-975,984,1313; bg_rgb = the last plane's own
+ *                                                colour under torgba_sep_background).  4x fewer HBM / PCIe bytes; output
+ *                                                identical to rendering the expanded stack.
+ *   camera, one of
+ *     ray_dir [V,3,H,W] + eye [V,3] + z_dir [V,3]   the reference's tensors (parity mode: bit-exact texel coordinates)
+ *     cam [V,16] = {focal, cx, cy, pixel-centre offset (0.5), R row-major (9), eye (3)}
+ *                                                fast mode: rays generated in the kernel with camera.py:53-118,182-211's
+ *                                                arithmetic (fp64 camera ray -> fp32 -> fp32 rotation); saves the [V,3,H,W]
+ *                                                tensor and its upload.  Forward only.
+ *   view_group  > 1 when every view_group consecutive views share one MPI (V % view_group == 0): tiles are then ordered so that
+ *               concurrently running CTAs work on the same texels (L2 reuse; video render, multi-view search).  0/1 otherwise.
+ *   outputs, one of
+ *     color [V,3,H,W] + depth [V,1,H,W]          fp32 (2c-1 with GMPI_COLOR_MINUS1_1)
+ *     peer_frames / n_peers / frame_offset       fused all-gather, see gmpi_mpi_render_fwd_gather.  A single NVLS multicast
+ *                                                address with n_peers = 1 makes the switch replicate the stores.
+ *     video_rgb [V,H,W,3] uint8 + video_depth [V,H,W,1] uint8 (optional), depth_near / depth_range
+ *                                                the conversion lines of render_video.py:118-126 fused into the store:
+ *                                                ((2c-1)+1)/2*255 truncated; clip((d - near)/range, 0, 1)*255 truncated
+ *                                                (GMPI_U8_ROUND_HALF_UP: torchvision save_image rounding instead)
+ *   transmittance [V,N,H,W]                      training forward: saved for gmpi_mpi_render_bwd_ex
+ *   backward: g_color [V,3,H,W], g_depth (nullable), and g_rgba [M,N,4,Ht,Wt]  or  g_rgb [M,3,Ht,Wt] (+ g_bg_rgb) + g_alpha
+ *             [M,N,1,Ht,Wt]; zeroed by the callee with GMPI_ZERO_GRAD, else accumulated into
+ */
+typedef struct gmpi_render_desc {
+    uint32_t struct_bytes;
+    uint32_t options;
+    int32_t M, V, N, Ht, Wt, H, W;
+    int32_t view_group;
+    int32_t n_peers, frame_offset;
+    float depth_near, depth_range;
+    const float* rgba;
+    const float* rgb;
+    const float* alpha;
+    const float* bg_rgb;
+    const int32_t* view2mpi;
+    const float* dhw;
+    const float* ray_dir;
+    const float* eye;
+    const float* z_dir;
+    const float* cam;
+    float* color;
+    float* depth;
+    float* transmittance;
+    float* const* peer_frames;
+    uint8_t* video_rgb;
+    uint8_t* video_depth;
+    const float* g_color;
+    const float* g_depth;
+    float* g_rgba;
+    float* g_rgb;
+    float* g_bg_rgb;
+    float* g_alpha;
+    uint32_t* flags;
+    void* stream;
+} gmpi_render_desc;
+
+int gmpi_mpi_render_fwd_ex(const gmpi_render_desc* desc);
+int gmpi_mpi_render_bwd_ex(const gmpi_render_desc* desc);
+/* Host-buffer form (end-to-end entry point, see gmpi_mpi_render_fwd_host): all pointers of *desc are HOST memory, `stream` is
+ * ignored, *flags receives the flag word.  Forward only; supports the factored MPI, cam and the video outputs. */
+int gmpi_mpi_render_host_ex(const gmpi_render_desc* desc, int device);
+
+/*
  * Range checks of MPIRenderer.render (mpi_renderer.py:447-449) and MPI.check_shapes
  * (mpi.py:185-187) in one streaming pass: sets GMPI_FLAG_RGBA_RANGE / GMPI_FLAG_ALPHA_RANGE.
  */
@@ -170,6 +244,12 @@ int gmpi_debug_plane_coords_packed(const int32_t* view2mpi, const float* dhw, co
 
 /* Test hook: force the forward kernel variant: 0 auto (default), 1 direct-gather, 2 TMA-staged. */
 int gmpi_debug_set_fwd_variant(int variant);
+
+/* Test hook (host only): tile order for a tile height (30 forward, 24 backward) and view grouping (gmpi_render_desc.view_group). */
+int gmpi_debug_tile_walk_ex(int H, int W, int V, int tile_h, int view_group, int grid, int cta, int* out_v_px0_py0, int max_tiles);
+
+/* Test hook: the rays the fast mode generates from cam [V,16] -> ray_dir [V,3,H,W] (device memory). */
+int gmpi_debug_cam_rays(const float* cam, float* ray_dir, int V, int H, int W, void* stream);
 
 /* Test hook (host only, no GPU work): the persistent kernels' tile order.  Writes the (view, px0, py0) of the tiles that
  * CTA `cta` of a `grid`-CTA launch walks, in order, into out_v_px0_py0[3 * max_tiles]; returns their number (>= 0) or a

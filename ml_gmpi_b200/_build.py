@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgmpi_mpi_render.so")
 SOURCES = ["mpi_render.cu"]
-HEADERS = ["mpi_common.cuh", "mpi_fwd_staged.cuh", "mpi_bwd_staged.cuh", "tma_utils.cuh", os.path.join("..", "..", "include", "gmpi_mpi_render.h")]
+HEADERS = ["mpi_common.cuh", "mpi_fwd_staged.cuh", "mpi_bwd_box.cuh", "tma_utils.cuh", os.path.join("..", "..", "include", "gmpi_mpi_render.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "1886",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -26,8 +26,37 @@ ABI_VERSION = 2
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
     "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed", "gmpi_debug_tile_walk",
-    "gmpi_mpi_render_fwd_plan",
+    "gmpi_mpi_render_fwd_plan", "gmpi_mpi_render_fwd_ex", "gmpi_mpi_render_bwd_ex", "gmpi_mpi_render_host_ex",
+    "gmpi_debug_tile_walk_ex", "gmpi_debug_cam_rays",
 ]
+
+OPT_U8_ROUND_HALF_UP = 16
+
+
+class RenderDesc(ctypes.Structure):
+    """gmpi_render_desc of include/gmpi_mpi_render.h (field for field)."""
+    _fields_ = [("struct_bytes", ctypes.c_uint32), ("options", ctypes.c_uint32),
+                ("M", ctypes.c_int32), ("V", ctypes.c_int32), ("N", ctypes.c_int32), ("Ht", ctypes.c_int32), ("Wt", ctypes.c_int32),
+                ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("view_group", ctypes.c_int32),
+                ("n_peers", ctypes.c_int32), ("frame_offset", ctypes.c_int32),
+                ("depth_near", ctypes.c_float), ("depth_range", ctypes.c_float)] + \
+               [(n, ctypes.c_void_p) for n in ("rgba", "rgb", "alpha", "bg_rgb", "view2mpi", "dhw", "ray_dir", "eye", "z_dir", "cam",
+                                               "color", "depth", "transmittance", "peer_frames", "video_rgb", "video_depth",
+                                               "g_color", "g_depth", "g_rgba", "g_rgb", "g_bg_rgb", "g_alpha", "flags", "stream")]
+
+
+def make_desc(**kw) -> RenderDesc:
+    """RenderDesc with struct_bytes set; tensors are passed as such (their data_ptr is taken), None -> NULL."""
+    d = RenderDesc()
+    d.struct_bytes = ctypes.sizeof(RenderDesc)
+    for k, v in kw.items():
+        if v is None:
+            continue
+        if hasattr(v, "data_ptr"):
+            v = v.data_ptr()
+        setattr(d, k, v)
+    return d
+
 
 _lib = None
 
@@ -81,6 +110,15 @@ def load():
     lib.gmpi_debug_set_fwd_variant.argtypes = [i]
     lib.gmpi_debug_tile_walk.restype = i
     lib.gmpi_debug_tile_walk.argtypes = [i, i, i, i, i, vp, i]
+    lib.gmpi_debug_tile_walk_ex.restype = i
+    lib.gmpi_debug_tile_walk_ex.argtypes = [i, i, i, i, i, i, i, vp, i]
+    lib.gmpi_debug_cam_rays.restype = i
+    lib.gmpi_debug_cam_rays.argtypes = [vp, vp, i, i, i, vp]
+    for fn in (lib.gmpi_mpi_render_fwd_ex, lib.gmpi_mpi_render_bwd_ex):
+        fn.restype = i
+        fn.argtypes = [ctypes.POINTER(RenderDesc)]
+    lib.gmpi_mpi_render_host_ex.restype = i
+    lib.gmpi_mpi_render_host_ex.argtypes = [ctypes.POINTER(RenderDesc), i]
     if lib.gmpi_abi_version() != ABI_VERSION:
         raise GmpiLibraryError(f"ABI mismatch: library {lib.gmpi_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

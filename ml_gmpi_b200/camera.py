@@ -58,6 +58,15 @@ class PinholeCamera:
         return rays.contiguous(), c2w[:, :3, 3].contiguous(), rot[:, :, 2].contiguous()
 
 
+def cam_params(c2w: torch.Tensor, focal: float, height: int, width: int, ray_from_pix_center: bool = True) -> torch.Tensor:
+    """[V,16] fp32 = {focal, cx, cy, pixel-centre offset, R row-major (9), eye (3)} per view: the `cam` input of the kernels' fast
+    mode (rays generated in the kernel with PinholeCamera's arithmetic instead of uploading ray_dir [V,3,H,W])."""
+    V = c2w.shape[0]
+    head = torch.tensor([float(focal), width / 2.0, height / 2.0, 0.5 if ray_from_pix_center else 0.0], dtype=torch.float32,
+                        device=c2w.device).expand(V, 4)
+    return torch.cat([head, c2w[:, :3, :3].reshape(V, 9).float(), c2w[:, :3, 3].float()], dim=1).contiguous()
+
+
 def truncated_normal(n: int, mean: float, std: float, n_std: float, generator: Optional[torch.Generator] = None):
     """Draw 4 normals per sample and keep the first inside mean +- n_std*std (gmpi/utils/torch_utils.py:51-76)."""
     tmp = torch.randn((n, 1, 4), generator=generator) * std + mean

@@ -1,0 +1,453 @@
+// Backward, TMA-staged persistent kernel with a tile-local gradient box: d(sum(color*g_color) + sum(depth*g_depth)) / d rgba.
+//
+// Planes are walked BACK TO FRONT with the forward's tile / ring / producer machinery (mpi_fwd_staged.cuh).  The forward, run
+// in training mode, saved the transmittance T_i in front of every plane ([V,N,H,W]); with it one sweep suffices:
+//     q_i = G.rgb_i + G_d*depth_i          d_i = q_i - R_i            (R_{N-1} = 0)
+//     dL/d rgb_i = G * a_i * T_i           dL/d a_i = T_i * d_i       R_{i-1} = R_i + a_i * d_i
+// which is autograd's  T_i q_i - (sum_{k>i} a_k q_k P_k) / (1 - a_i + 1e-10)  (cumprod_backward) without the division
+// (1e-10 when a_i == 1) and without cancellation; grid_sampler_2d_backward then scatters every value through the four bilinear
+// weights.
+//
+// Where the scatter goes (round 2).  Round 1 issued 16 red.global.add.f32 per (pixel, plane): 46 M REDG warp instructions per
+// view, each wrapped in BSSY/BRA/BSYNC when predicated, 64-bit address arithmetic, shuffles for tap hand-over -- 900 SASS
+// instructions per thread and plane, 28 % of the HBM roofline.  Measured on this part (profiles/r02_l2_reduce_probe.txt):
+// shared-memory fp32 atomics are a CAS loop (5.8 cycles per warp instruction), native INTEGER shared atomics run at 1.0, and a
+// dense, coalesced red.global of the finished sums is bound only by the DRAM read-modify-write of the gradient.  Hence:
+//   * every (tile, plane) has a GRADIENT BOX in shared memory with exactly the layout of the staged plane box
+//     ([row][channel][x], same index as the taps);
+//   * consumers add their 16 contributions per pixel with `red.shared.add.s32` on FIXED-POINT values: c * 2^(21-e) rounded to
+//     nearest (one FFMA against the 1.5*2^23 constant), where 2^e bounds every contribution of the tile (computed from the
+//     tile's upstream gradients, see tile_scale_exponent).  22 bits per contribution relative to that bound, exact (order
+//     independent) integer sums -- the accumulation is more repeatable than fp32 atomics and well inside the 1e-4 bar;
+//   * three FLUSHER warps convert a finished box to fp32 and add it to g_rgba with coalesced `red.global.add.v4.f32`
+//     (skipping all-zero quads and texels outside the texture) and re-zero it, while the consumers fill the other box.
+// Out-of-texture taps need no predication: they land in box cells that lie outside the texture, which the flush drops
+// (padding_mode="zeros").  A warp whose footprints do not all lie inside the staged box (non-projective rays, oversized
+// footprints, planes outside the exact-division range) samples global memory and scatters with red.global.add.f32 directly,
+// as the direct kernel does: results never depend on the producer's footprint estimate.
+#pragma once
+#include "mpi_fwd_staged.cuh"
+
+namespace gmpi {
+
+constexpr int kBwdConsWarps = 12, kBwdFlushWarps = 3;
+constexpr int kBwdTileH = kPairs * kBwdConsWarps;                                   // 64 x 24 pixel tiles
+constexpr int kBwdConsThreads = kBwdConsWarps * 32;
+constexpr int kBwdThreads = (kBwdConsWarps + 1 + kBwdFlushWarps) * 32;              // 16 warps: 12 consumers, producer, 3 flushers
+constexpr int kBwdStages = 2, kBwdBoxes = 2;
+constexpr int kBwdMaxBH = (((kBwdTileH * 5) / 4 + 6 + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp;
+constexpr int kBwdPlaneFloats = kMaxBW * kBwdMaxBH * 4;
+constexpr int kBwdTFloats = kTileW * kBwdTileH;
+constexpr int kBwdStride = kBwdPlaneFloats + kBwdTFloats;
+constexpr size_t kBwdSmem = (size_t)(kBwdStages * kBwdStride + kBwdBoxes * kBwdPlaneFloats) * 4 + (size_t)kMaxPlanesStaged * 32;
+static_assert(kBwdSmem + 1024 <= 227 * 1024, "backward ring + gradient boxes + plane table must fit one SM");
+
+struct BwdRing {
+    static constexpr int kTileRows = kBwdTileH, kRingStages = kBwdStages, kBoxMaxH = kBwdMaxBH;
+    static constexpr int kPlaneFloats = kBwdPlaneFloats, kStride = kBwdStride;
+    static constexpr bool kReverse = true;       // planes back to front; each stage also carries the tile's saved transmittance
+};
+
+struct GradPairs {
+    f2 g0[kPairs], g1[kPairs], g2[kPairs], gs[kPairs];   // upstream colour gradient and g_depth * (ray . z_dir)
+};
+
+// what the flushers need to know about a finished gradient box
+struct __align__(16) GradMeta {
+    int bx0, by0;        // texel coordinates of box element [0][.][0]
+    int rows, cls;       // staged rows (0: nothing in the box), width class (bw = kMinBW + cls * kBWStep)
+    int plane;           // m * N + i
+    float scale;         // 2^(e-21): fixed point -> fp32
+    int mpi, bg;         // factored MPI: m, and whether this plane's colour gradient goes to g_bg_rgb (last plane)
+};
+constexpr int kBwdAlphaOff = 3 * kMaxBW * kBwdMaxBH;     // factored MPI: alpha box behind the colour box (floats / ints)
+
+// red.global.add.f32 without a return value
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Scatter one pixel's four channel gradients through its bilinear footprint straight into global memory
+// (grid_sampler_2d_backward); the rare path of a warp whose footprints are not all inside the staged box.
+__device__ __noinline__ void scatter_pixel_global(const GradChans gch, int Wt, int Ht, int x0, int y0, float v0, float v1,
+                                                  float v2, float v3, float w00, float w01, float w10, float w11) {
+    const bool vx0 = (unsigned)x0 < (unsigned)Wt, vx1 = (unsigned)(x0 + 1) < (unsigned)Wt;
+    const bool vy0 = (unsigned)y0 < (unsigned)Ht, vy1 = (unsigned)(y0 + 1) < (unsigned)Ht;
+    const long long o = (long long)y0 * Wt + x0;
+    const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float* b0 = gch.c[c] + o;
+        if (vx0 && vy0) red_add(b0, v[c] * w00);
+        if (vx1 && vy0) red_add(b0 + 1, v[c] * w01);
+        if (vx0 && vy1) red_add(b0 + Wt, v[c] * w10);
+        if (vx1 && vy1) red_add(b0 + Wt + 1, v[c] * w11);
+    }
+}
+
+// Fixed-point exponent of a tile: every contribution c of the tile satisfies |c| <= 4 * qmax < 2^e, where
+// qmax = max over the tile's pixels of |G_r| + |G_g| + |G_b| + |G_d (ray . z_dir)| * max_i |scale_i|:
+//   |dL/d rgb contribution| = |G_c| a T w <= qmax;   |dL/d a contribution| = T |q - R| w <= 2 qmax   (rgb, a, T, w in [0,1];
+//   R is a sub-convex combination of the q's) -- and a factor 2 of slack for inputs that leave [0,1] by rounding.
+// Contributions are rounded to multiples of 2^(e-21), so |c| * 2^(21-e) < 2^21 and a texel may collect 2^9 of them in int32.
+__device__ __forceinline__ int tile_scale_exponent(float qmax) {
+    const float b = 4.0f * qmax;
+    if (!(b > 0.0f)) return 0;
+    int e = (int)((__float_as_uint(b) >> 23) & 0xffu) - 126;     // 2^e > b  (b = 1.m * 2^(E-127) < 2^(E-126))
+    return max(-100, min(100, e));
+}
+
+// Fast body: four pixels (two packed pairs) from a staged box of compile-time width BW, contributions into the gradient box.
+// Returns false (nothing sampled, R unchanged) if any footprint is not inside the box.
+// AOFF as in sample_pairs: 0 = expanded stage, > 0 = factored (colour box [row][3][BW], alpha box [row][BW] at AOFF).
+template <int BW, int AOFF = 0>
+__device__ __forceinline__ bool bwd_box_pairs(const float* __restrict__ sb, int cx, int cy, int rows2, const CoordPairs& c,
+                                              const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], int (&idx)[kPix], int (&jdx)[kPix],
+                                              f2 (&w4)[kPairs][4], f2 (&val)[kPairs][4]) {
+    constexpr int RP = AOFF ? 3 * BW : 4 * BW, AP = AOFF ? BW : 4 * BW, A0 = AOFF ? AOFF : 3 * BW;
+    const f2 m1 = splat(-1.0f), one = splat(1.0f);
+    const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
+    f2 fx0[kPairs], fy0[kPairs];
+    bool inbox = true;
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 tx = add2_rm(c.ix[P], magic), ty = add2_rm(c.iy[P], magic);
+        fx0[P] = add2(tx, nmagic);
+        fy0[P] = add2(ty, nmagic);
+        const int rxa = __float_as_int(tx.x) - cx, rxb = __float_as_int(tx.y) - cx;
+        const int rya = __float_as_int(ty.x) - cy, ryb = __float_as_int(ty.y) - cy;
+        inbox = inbox && (unsigned)rxa <= (unsigned)(BW - 2) && (unsigned)rxb <= (unsigned)(BW - 2) &&
+                (unsigned)rya <= (unsigned)rows2 && (unsigned)ryb <= (unsigned)rows2;
+        idx[2 * P] = rya * RP + rxa;
+        idx[2 * P + 1] = ryb * RP + rxb;
+        if (AOFF) { jdx[2 * P] = rya * AP + rxa + A0; jdx[2 * P + 1] = ryb * AP + rxb + A0; }     // separate alpha box
+    }
+    if (!__all_sync(0xffffffffu, inbox)) return false;   // warp-uniform
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+        const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);
+        const f2 wy0 = fma2(wy1, m1, one);
+        const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
+        const float* ta = sb + idx[2 * P];
+        const float* tb = sb + idx[2 * P + 1];
+#define GMPI_TAP(ch)                                                                                           \
+    fma2(make_float2(ta[RP + ch * BW + 1], tb[RP + ch * BW + 1]), w11,                                         \
+         fma2(make_float2(ta[RP + ch * BW], tb[RP + ch * BW]), w10,                                            \
+              fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
+        const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2);
+#undef GMPI_TAP
+        const float* aa = AOFF ? sb + jdx[2 * P] : ta + A0;
+        const float* ab = AOFF ? sb + jdx[2 * P + 1] : tb + A0;
+        const f2 a = fma2(make_float2(aa[AP + 1], ab[AP + 1]), w11,
+                          fma2(make_float2(aa[AP], ab[AP]), w10, fma2(make_float2(aa[1], ab[1]), w01, mul2(make_float2(aa[0], ab[0]), w00))));
+        const f2 q = fma2(G.g0[P], r, fma2(G.g1[P], g, fma2(G.g2[P], b, mul2(G.gs[P], c.sc[P]))));
+        const f2 d = fma2(R[P], m1, q);                 // q - R
+        const f2 w = mul2(a, T[P]);
+        R[P] = fma2(a, d, R[P]);
+        val[P][0] = mul2(G.g0[P], w); val[P][1] = mul2(G.g1[P], w); val[P][2] = mul2(G.g2[P], w);
+        val[P][3] = mul2(T[P], d);                      // dL/d alpha
+        w4[P][0] = w00; w4[P][1] = w01; w4[P][2] = w10; w4[P][3] = w11;
+    }
+    return true;
+}
+
+// The 64 fixed-point adds of a thread's four pixels into the gradient box (`gb` has the staged box's layout).
+template <int BW, int AOFF = 0>
+__device__ __forceinline__ void box_scatter(int* __restrict__ gb, const int (&idx)[kPix], const int (&jdx)[kPix], const f2 (&w4)[kPairs][4],
+                                            const f2 (&val)[kPairs][4], f2 Fs) {
+    constexpr int RP = AOFF ? 3 * BW : 4 * BW, AP = AOFF ? BW : 4 * BW;
+    const f2 magic = splat(kFloorMagic);
+#pragma unroll
+    for (int P = 0; P < kPairs; ++P) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            int* ga = gb + ((AOFF && ch == 3) ? jdx[2 * P] : idx[2 * P] + ch * BW);
+            int* gq = gb + ((AOFF && ch == 3) ? jdx[2 * P + 1] : idx[2 * P + 1] + ch * BW);
+            const int pitch = ch < 3 ? RP : AP;
+            const f2 vF = mul2(val[P][ch], Fs);                      // exact (power of two)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // RN(vF * w) as an integer in the mantissa of t (|vF * w| < 2^21): one packed FFMA for two pixels
+                const f2 t = fma2(vF, w4[P][k], magic);
+                const int off = (k & 1) + (k >> 1) * pitch;
+                atomicAdd(ga + off, __float_as_int(t.x) - kFloorMagicBits);
+                atomicAdd(gq + off, __float_as_int(t.y) - kFloorMagicBits);
+            }
+        }
+    }
+}
+
+// Flusher: rows fw, fw + 3, ... of a finished gradient box -> fp32 -> red.global.add.v4.f32, then zero.
+template <int BW, bool FAC>
+__device__ __forceinline__ void flush_box(int* __restrict__ gb, const GradMeta& gm, const RenderParams& p, size_t tex, int Ht, int Wt,
+                                          int fw, int lane) {
+    constexpr int Q = BW / 4;      // float4 quads per channel row
+    // destination slabs of the four channels
+    float* dst[4];
+    if (FAC) {
+        float* rgb = (gm.bg ? p.g_bg_rgb : p.g_rgb) + (size_t)gm.mpi * 3 * tex;
+        dst[0] = rgb; dst[1] = rgb + tex; dst[2] = rgb + 2 * tex; dst[3] = p.g_alpha + (size_t)gm.plane * tex;
+    } else {
+        float* b = p.g_rgba + (size_t)gm.plane * 4 * tex;
+        dst[0] = b; dst[1] = b + tex; dst[2] = b + 2 * tex; dst[3] = b + 3 * tex;
+    }
+    const float sc = gm.scale;
+    for (int r = fw; r < gm.rows; r += kBwdFlushWarps) {
+        const int ty = gm.by0 + r;                                   // warp-uniform
+        const bool row_ok = (unsigned)ty < (unsigned)Ht;
+        // BW quads per box row: channel ch, quad x4.  Expanded: [row][4][BW]; factored: [row][3][BW] + alpha box [row][BW].
+        int4* crow = reinterpret_cast<int4*>(gb + r * (FAC ? 3 * BW : 4 * BW));
+        int4* arow = reinterpret_cast<int4*>(gb + (FAC ? kBwdAlphaOff + r * BW : r * 4 * BW + 3 * BW));
+        for (int j = lane; j < BW; j += 32) {
+            const int ch = j / Q, x4 = j - ch * Q;
+            int4* cell = ch < 3 ? crow + j : arow + x4;
+            const int4 a = *cell;
+            if ((a.x | a.y | a.z | a.w) == 0) continue;              // untouched halo: nothing to add, nothing to clear
+            *cell = make_int4(0, 0, 0, 0);
+            const int tx = gm.bx0 + 4 * x4;
+            if (row_ok && (unsigned)tx < (unsigned)Wt) {             // bx0 % 4 == 0 and Wt % 4 == 0: a quad is inside or outside as a whole
+                float* d = ch == 0 ? dst[0] : ch == 1 ? dst[1] : ch == 2 ? dst[2] : dst[3];
+                red_add_v4(d + (size_t)ty * Wt + tx, (float)a.x * sc, (float)a.y * sc, (float)a.z * sc, (float)a.w * sc);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void bwd_consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBwdConsThreads) : "memory"); }
+
+template <bool kAlignCorners, bool kFactored>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* s_buf = reinterpret_cast<float*>(smem_raw);                                          // rgba ring (+ transmittance boxes)
+    int* s_grad = reinterpret_cast<int*>(smem_raw + (size_t)kBwdStages * kBwdStride * 4);       // gradient boxes
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)(kBwdStages * kBwdStride + kBwdBoxes * kBwdPlaneFloats) * 4);
+    __shared__ StageMeta s_meta[kBwdStages];
+    __shared__ GradMeta s_gmeta[kBwdBoxes];
+    __shared__ __align__(8) uint64_t s_full[kBwdStages], s_empty[kBwdStages], g_full[kBwdBoxes], g_empty[kBwdBoxes];
+    __shared__ TileWalk s_walk;
+    __shared__ unsigned s_qmax[3];        // per-tile bound (bits of a non-negative float), three slots in rotation
+    __shared__ unsigned s_zmax;           // max_i |z_diff_i| of the current view's plane table
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        s_walk.init(tiles_x, p.H, p.V, (int)blockIdx.x, (int)gridDim.x, kBwdTileH, p.view_group);
+        for (int s = 0; s < kBwdStages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kBwdConsWarps);
+        }
+        for (int s = 0; s < kBwdBoxes; ++s) {
+            mbar_init(&g_full[s], kBwdConsWarps);
+            mbar_init(&g_empty[s], kBwdFlushWarps);
+        }
+        s_qmax[0] = s_qmax[1] = s_qmax[2] = 0u;
+        s_zmax = 0u;
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < kBwdBoxes * kBwdPlaneFloats; i += kBwdThreads) s_grad[i] = 0;
+    __syncthreads();
+
+    const int Ht = p.Ht, Wt = p.Wt, N = p.N;
+    const size_t tex = (size_t)Ht * Wt;
+
+    if (warp == kBwdConsWarps) {
+        // ================================ producer ================================
+        if (lane == 0) tma_prefetch_desc(&maps.t);
+        staged_producer<kAlignCorners, BwdRing>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
+    } else if (warp > kBwdConsWarps) {
+        // ================================ flushers ================================
+        const int fw = warp - kBwdConsWarps - 1;
+        int f_box = 0;
+        uint32_t f_phase = 0;
+        TileXY txy;
+        for (int j = 0; s_walk.at(j, txy); ++j) {
+            for (int ii = 0; ii < N; ++ii) {
+                const int b = f_box;
+                const uint32_t ph = f_phase;
+                if (++f_box == kBwdBoxes) { f_box = 0; f_phase ^= 1u; }
+                mbar_wait(&g_full[b], ph);
+                const GradMeta gm = s_gmeta[b];
+                int* gb = s_grad + b * kBwdPlaneFloats;
+                if (gm.rows > 0) {
+                    switch (gm.cls) {     // warp-uniform
+                        case 0: flush_box<56, kFactored>(gb, gm, p, tex, Ht, Wt, fw, lane); break;
+                        case 1: flush_box<64, kFactored>(gb, gm, p, tex, Ht, Wt, fw, lane); break;
+                        case 2: flush_box<72, kFactored>(gb, gm, p, tex, Ht, Wt, fw, lane); break;
+                        case 3: flush_box<80, kFactored>(gb, gm, p, tex, Ht, Wt, fw, lane); break;
+                        default: flush_box<88, kFactored>(gb, gm, p, tex, Ht, Wt, fw, lane); break;
+                    }
+                }
+                __syncwarp();
+                mbar_arrive_if(&g_empty[b], lane == 0);
+            }
+        }
+    } else {
+        // ================================ consumers ================================
+        const float fWt = (float)Wt, fHt = (float)Ht;
+        const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+        const size_t img = (size_t)p.H * p.W;
+        int c_stage = 0, g_box = 0;
+        uint32_t c_phase = 0, g_phase = 0;
+        const float gscale = (p.options & GMPI_COLOR_MINUS1_1) ? 2.0f : 1.0f;   // upstream gradient is w.r.t. 2*color-1
+        int v_table = -1;
+        TileXY txy;
+        for (int j = 0; s_walk.at(j, txy); ++j) {
+            const int v = txy.v, px0 = txy.px0, py0 = txy.py0;
+            const int m = __ldg(p.view2mpi + v);
+            const float* e = p.eye + 3 * v;
+            const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
+            const float zd[3] = {__ldg(p.z_dir + 3 * v), __ldg(p.z_dir + 3 * v + 1), __ldg(p.z_dir + 3 * v + 2)};
+            if (v != v_table) {          // (view, plane) constants, once per view and CTA
+                bwd_consumer_bar_sync();
+                if (threadIdx.x == 0) s_zmax = 0u;
+                bwd_consumer_bar_sync();
+                float zm = 0.0f;
+                for (int i = threadIdx.x; i < N; i += kBwdConsThreads) {
+                    const PlaneConst pc = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
+                    s_pc[i] = pc;
+                    zm = fmaxf(zm, fabsf(pc.z_diff));
+                }
+                atomicMax(&s_zmax, __float_as_uint(zm));
+                bwd_consumer_bar_sync();
+                v_table = v;
+            }
+            // ---- per-pixel inputs (clamped into the image; the tile overhang carries zero upstream gradient) ----
+            const float* rays = p.ray_dir + (size_t)v * 3 * img;
+            RayConst rc[kPix];
+            RayPairs rp;
+            GradPairs G;
+            float gq[kPix][4];
+            bool rays_fast = (in_safe_range(ev[0]) || ev[0] == 0.0f) && (in_safe_range(ev[1]) || ev[1] == 0.0f);
+            const float zmax = __uint_as_float(s_zmax);
+            float qmax = 0.0f;
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) {
+                const int pxq = px0 + lane + 32 * (q & 1), pyq = py0 + kPairs * warp + (q >> 1);
+                const bool valid = pxq < p.W && pyq < p.H;
+                const size_t pix = (size_t)min(pyq, p.H - 1) * p.W + min(pxq, p.W - 1);
+                const float* rd = rays + pix;
+                rc[q] = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+                rays_fast = rays_fast && rc[q].fast && fabsf(rc[q].rx2) <= 0x1p40f && fabsf(rc[q].ry2) <= 0x1p40f;
+                const float* gc = p.g_color + (size_t)v * 3 * img + pix;
+                gq[q][0] = valid ? gscale * __ldg(gc) : 0.0f;
+                gq[q][1] = valid ? gscale * __ldg(gc + img) : 0.0f;
+                gq[q][2] = valid ? gscale * __ldg(gc + 2 * img) : 0.0f;
+                gq[q][3] = (valid && p.g_depth) ? __ldg(p.g_depth + (size_t)v * img + pix) * rc[q].dz : 0.0f;
+                qmax = fmaxf(qmax, fabsf(gq[q][0]) + fabsf(gq[q][1]) + fabsf(gq[q][2]) + fabsf(gq[q][3]) * (zmax * fabsf(rc[q].yrz)));
+            }
+            // ---- the tile's fixed-point scale: max over all consumer threads (three slots in rotation, see below) ----
+            {
+                const int slot = j % 3;
+                for (int o = 16; o > 0; o >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+                if (!(qmax < 0x1p100f)) qmax = 0x1p100f;             // inf/NaN upstream gradients: keep the exponent finite
+                if (lane == 0) atomicMax(&s_qmax[slot], __float_as_uint(qmax));
+                if (threadIdx.x == 0) s_qmax[(j + 1) % 3] = 0u;       // next tile's slot: its last readers passed the previous tile's barrier
+                bwd_consumer_bar_sync();
+                qmax = __uint_as_float(s_qmax[slot]);
+            }
+            const int e_fix = tile_scale_exponent(qmax);
+            const f2 Fs = splat(__uint_as_float((unsigned)(127 + 21 - e_fix) << 23));      // 2^(21-e)
+            const float inv_scale = __uint_as_float((unsigned)(127 - 21 + e_fix) << 23);    // 2^(e-21)
+
+            const bool idle = py0 + kPairs * warp >= p.H;      // warp-uniform: no row of this warp is inside the image
+#pragma unroll
+            for (int P = 0; P < kPairs; ++P) {
+                rp.rx2[P] = make_float2(rc[2 * P].rx2, rc[2 * P + 1].rx2);
+                rp.ry2[P] = make_float2(rc[2 * P].ry2, rc[2 * P + 1].ry2);
+                rp.nrz[P] = make_float2(-rc[2 * P].rz, -rc[2 * P + 1].rz);
+                rp.yrz[P] = make_float2(rc[2 * P].yrz, rc[2 * P + 1].yrz);
+                G.g0[P] = make_float2(gq[2 * P][0], gq[2 * P + 1][0]);
+                G.g1[P] = make_float2(gq[2 * P][1], gq[2 * P + 1][1]);
+                G.g2[P] = make_float2(gq[2 * P][2], gq[2 * P + 1][2]);
+                G.gs[P] = make_float2(gq[2 * P][3], gq[2 * P + 1][3]);
+            }
+            const f2 ex2 = splat(rc[0].ex2), ey2 = splat(rc[0].ey2), hsx2 = splat(hsx), hsy2 = splat(hsy);
+            const bool warp_fast = __all_sync(0xffffffffu, rays_fast) && !idle;
+            f2 R[kPairs];
+#pragma unroll
+            for (int P = 0; P < kPairs; ++P) R[P] = splat(0.0f);
+            for (int ii = 0; ii < N; ++ii) {
+                const int i = N - 1 - ii;
+                const int s = c_stage, b = g_box;
+                const uint32_t ph = c_phase, gph = g_phase;
+                if (++c_stage == kBwdStages) { c_stage = 0; c_phase ^= 1u; }
+                if (++g_box == kBwdBoxes) { g_box = 0; g_phase ^= 1u; }
+                const PlaneConst pcc = s_pc[i];
+                CoordPairs cc;
+                if (warp_fast) coords_pairs<kAlignCorners>(pcc, rp, ex2, ey2, hsx2, hsy2, fWt, fHt, cc);
+                mbar_wait(&s_full[s], ph);
+                const StageMeta mt = s_meta[s];
+                const float* sb = s_buf + s * kBwdStride;
+                const int sel = mt.sel;
+                f2 T[kPairs];      // transmittance saved by the forward, staged next to the plane tile: [kBwdTileH][kTileW]
+#pragma unroll
+                for (int P = 0; P < kPairs; ++P) {
+                    const float* tr = sb + kBwdPlaneFloats + (kPairs * warp + P) * kTileW + lane;
+                    T[P] = make_float2(tr[0], tr[32]);
+                }
+                int idx[kPix], jdx[kPix];
+                f2 w4[kPairs][4], val[kPairs][4];
+                constexpr int AO = kFactored ? kBwdAlphaOff : 0;
+                int cls = -1;
+                if (warp_fast) {   // warp-uniform, one-hot class
+                    if (sel & (1 << 18)) cls = bwd_box_pairs<72, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 2 : -1;
+                    else if (sel & (1 << 17)) cls = bwd_box_pairs<64, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 1 : -1;
+                    else if (sel & (1 << 19)) cls = bwd_box_pairs<80, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 3 : -1;
+                    else if (sel & (1 << 16)) cls = bwd_box_pairs<56, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 0 : -1;
+                    else if (sel & (1 << 20)) cls = bwd_box_pairs<88, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 4 : -1;
+                }
+                __syncwarp();
+                mbar_arrive_if(&s_empty[s], lane == 0);     // taps and transmittance are in registers: hand the stage back
+                // ---- gradient box of this (tile, plane): wait until the flushers have emptied it ----
+                mbar_wait(&g_empty[b], gph ^ 1u);
+                int* gb = s_grad + b * kBwdPlaneFloats;
+                if (cls == 2) box_scatter<72, AO>(gb, idx, jdx, w4, val, Fs);
+                else if (cls == 1) box_scatter<64, AO>(gb, idx, jdx, w4, val, Fs);
+                else if (cls == 3) box_scatter<80, AO>(gb, idx, jdx, w4, val, Fs);
+                else if (cls == 0) box_scatter<56, AO>(gb, idx, jdx, w4, val, Fs);
+                else if (cls == 4) box_scatter<88, AO>(gb, idx, jdx, w4, val, Fs);
+                if (warp == 0 && lane == 0) {               // (warp 0 always has a row inside the image)
+                    GradMeta gm;
+                    const int mode = (sel >> 8) & 3;
+                    gm.bx0 = mt.cx - kFloorMagicBits; gm.by0 = mt.cy - kFloorMagicBits;
+                    gm.rows = mode == 0 ? mt.rows2 + 2 : 0;
+                    gm.cls = ((sel & 0xff) - kMinBW) / kBWStep;
+                    gm.plane = m * N + i;
+                    gm.scale = inv_scale;
+                    gm.mpi = m; gm.bg = (kFactored && p.g_bg_rgb && i == N - 1) ? 1 : 0;
+                    s_gmeta[b] = gm;
+                }
+                __syncwarp();
+                mbar_arrive_if(&g_full[b], lane == 0);
+                if (cls < 0 && !idle) {
+                    // ---- generic body (rare): per-pixel checks, sampling and scattering straight in global memory.  Also
+                    // taken when the producer's corner-ray estimate says "nothing under the tile": a hint, never trusted ----
+                    const PlaneChans plane = plane_chans(p, m, i, tex);
+                    const GradChans gplane = grad_chans(p, m, i, tex);
+                    float* Rs = reinterpret_cast<float*>(R);
+                    const float* Ts = reinterpret_cast<const float*>(T);
+#pragma unroll
+                    for (int q = 0; q < kPix; ++q) {
+                        const int qq = (q & 1) + 2 * (q >> 1);      // R / T are stored as pairs: element (P, half) = 2 P + half
+                        RayConst rg = rc[q];
+                        rg.fast = false;
+                        const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
+                        if (!coord_hits(tc.ix, tc.iy, fWt, fHt)) continue;
+                        const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
+                        const float fx = floorf(tc.ix), fy = floorf(tc.iy);
+                        const float wx1 = tc.ix - fx, wy1 = tc.iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+                        const float qv = fmaf(gq[q][0], sv.x, fmaf(gq[q][1], sv.y, fmaf(gq[q][2], sv.z, gq[q][3] * tc.scale)));
+                        const float d = qv - Rs[qq];
+                        const float w = sv.w * Ts[qq];
+                        Rs[qq] = fmaf(sv.w, d, Rs[qq]);
+                        scatter_pixel_global(gplane, Wt, Ht, (int)fx, (int)fy, gq[q][0] * w, gq[q][1] * w, gq[q][2] * w, Ts[qq] * d,
+                                             wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace gmpi

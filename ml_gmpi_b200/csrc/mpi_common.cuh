@@ -32,11 +32,115 @@ struct RenderParams {
     int n_peers, frame_offset;
     // training: transmittance before each plane, [V,N,H,W]; written by the forward, read by the staged backward (nullable)
     float* transmittance;
+    // fast mode (opt-in): rays generated in the kernel from the pinhole camera of each view instead of read from ray_dir
+    // (camera.py:182-211).  cam [V,16] = {focal, cx, cy, pixel-centre offset, R row-major (9), eye (3)}; ray_dir may be NULL
+    const float* cam;
+    // video epilogue (opt-in, render_video.py:118-126): uint8 HWC colour [V,H,W,3] and depth [V,H,W,1] instead of color/depth
+    uint8_t* video_rgb;
+    uint8_t* video_depth;
+    float depth_near, depth_range;
+    // factored MPI (opt-in, networks_cond_on_pos_enc.py:950-975): shared colour rgb [M,3,Ht,Wt] (+ bg_rgb for the last plane) and
+    // per-plane alpha [M,N,1,Ht,Wt] instead of rgba
+    const float* rgb;
+    const float* bg_rgb;
+    const float* alpha;
+    float* g_rgb;             // bwd, factored: [M,3,Ht,Wt] (sum over planes 0..N-1, or 0..N-2 when bg_rgb is given)
+    float* g_bg_rgb;          // bwd, factored with a separate background: [M,3,Ht,Wt] of the last plane
+    float* g_alpha;           // bwd, factored: [M,N,1,Ht,Wt]
+    int view_group;           // > 1: every `view_group` consecutive views share one MPI (tile order hint, see TileWalk)
 };
 
+// The four channel slabs (Ht*Wt floats each) of one (MPI, plane): expanded rgba or the generator's factored form.
+struct PlaneChans { const float* c[4]; };
+__device__ __forceinline__ PlaneChans plane_chans(const RenderParams& p, int m, int i, size_t tex) {
+    PlaneChans pc;
+    if (p.alpha) {
+        const float* rgb = ((p.bg_rgb && i == p.N - 1) ? p.bg_rgb : p.rgb) + (size_t)m * 3 * tex;
+        pc.c[0] = rgb; pc.c[1] = rgb + tex; pc.c[2] = rgb + 2 * tex;
+        pc.c[3] = p.alpha + ((size_t)m * p.N + i) * tex;
+    } else {
+        const float* b = p.rgba + ((size_t)m * p.N + i) * 4 * tex;
+        pc.c[0] = b; pc.c[1] = b + tex; pc.c[2] = b + 2 * tex; pc.c[3] = b + 3 * tex;
+    }
+    return pc;
+}
+struct GradChans { float* c[4]; };
+__device__ __forceinline__ GradChans grad_chans(const RenderParams& p, int m, int i, size_t tex) {
+    GradChans gc;
+    if (p.g_alpha) {
+        float* rgb = ((p.g_bg_rgb && i == p.N - 1) ? p.g_bg_rgb : p.g_rgb) + (size_t)m * 3 * tex;
+        gc.c[0] = rgb; gc.c[1] = rgb + tex; gc.c[2] = rgb + 2 * tex;
+        gc.c[3] = p.g_alpha + ((size_t)m * p.N + i) * tex;
+    } else {
+        float* b = p.g_rgba + ((size_t)m * p.N + i) * 4 * tex;
+        gc.c[0] = b; gc.c[1] = b + tex; gc.c[2] = b + 2 * tex; gc.c[3] = b + 3 * tex;
+    }
+    return gc;
+}
+
+// internal option bits (above the public GMPI_* bits of include/gmpi_mpi_render.h)
+constexpr uint32_t kOptVec4Stores = 1u << 16;   // W % 4 == 0 and all output bases 16-byte aligned: float4 epilogue stores
+
+// Pinhole ray of pixel (px, py) of a view, the arithmetic of ml_gmpi_b200.camera.PinholeCamera (camera.py:53-76,98-118,182-211
+// of the reference): camera-space direction in fp64, normalised, rounded to fp32, rotated to world space in fp32.
+__device__ __forceinline__ void cam_ray(const float* __restrict__ cam, int px, int py, float& rx, float& ry, float& rz) {
+    const double focal = (double)__ldg(cam), cx = (double)__ldg(cam + 1), cy = (double)__ldg(cam + 2), off = (double)__ldg(cam + 3);
+    const double xs = __ddiv_rn(__dsub_rn(__dadd_rn((double)px, off), cx), focal);      // K^-1 [u v 1], camera.py:63-66
+    const double ys = __ddiv_rn(__dsub_rn(__dadd_rn((double)py, off), cy), focal);
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xs, xs), __dmul_rn(ys, ys)), 1.0));   // camera.py:98-105
+    const float dx = (float)__ddiv_rn(xs, nrm), dy = (float)__ddiv_rn(ys, nrm), dz = (float)__ddiv_rn(1.0, nrm);    // :116-118
+    const float* R = cam + 4;
+    rx = fmaf(__ldg(R + 2), dz, fmaf(__ldg(R + 1), dy, __ldg(R + 0) * dx));                 // ray_dir = R @ rays, camera.py:201
+    ry = fmaf(__ldg(R + 5), dz, fmaf(__ldg(R + 4), dy, __ldg(R + 3) * dx));
+    rz = fmaf(__ldg(R + 8), dz, fmaf(__ldg(R + 7), dy, __ldg(R + 6) * dx));
+}
+
+// Ray of pixel (px, py) of view v: read from ray_dir (the reference's tensor: parity mode) or generated (fast mode).
+__device__ __forceinline__ void load_ray(const RenderParams& p, int v, int px, int py, size_t img, float& rx, float& ry, float& rz) {
+    if (p.cam) {
+        cam_ray(p.cam + 16 * (size_t)v, px, py, rx, ry, rz);
+    } else {
+        const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)py * p.W + px;
+        rx = __ldg(rd); ry = __ldg(rd + img); rz = __ldg(rd + 2 * img);
+    }
+}
+// eye and optical axis of view v (camera.py:189-190,209)
+__device__ __forceinline__ void load_eye_z(const RenderParams& p, int v, float (&ev)[3], float (&zd)[3]) {
+    if (p.cam) {
+        const float* c = p.cam + 16 * (size_t)v;
+        ev[0] = __ldg(c + 13); ev[1] = __ldg(c + 14); ev[2] = __ldg(c + 15);
+        zd[0] = __ldg(c + 6); zd[1] = __ldg(c + 9); zd[2] = __ldg(c + 12);     // R[:, 2]
+    } else {
+        ev[0] = __ldg(p.eye + 3 * v); ev[1] = __ldg(p.eye + 3 * v + 1); ev[2] = __ldg(p.eye + 3 * v + 2);
+        zd[0] = __ldg(p.z_dir + 3 * v); zd[1] = __ldg(p.z_dir + 3 * v + 1); zd[2] = __ldg(p.z_dir + 3 * v + 2);
+    }
+}
+
+// uint8 conversions of the reference's consumers.  Truncating: render_video.py:119-126 (numpy astype(uint8)); rounding:
+// torchvision save_image(normalize=True, range=(-1,1)) as used by fid_evaluation.py:125-130 (mul(255).add_(0.5).clamp_(0,255)).
+__device__ __forceinline__ uint8_t color_to_u8(float img_m11, bool round_half_up) {
+    if (round_half_up) {
+        const float c = fminf(fmaxf(img_m11, -1.0f), 1.0f);
+        const float x = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(c, 1.0f), 2.0f), 255.0f), 0.5f);
+        return (uint8_t)(int)fminf(fmaxf(x, 0.0f), 255.0f);
+    }
+    return (uint8_t)(int)__fmul_rn(__fmul_rn(__fadd_rn(img_m11, 1.0f), 0.5f), 255.0f);       // (img + 1) / 2.0 * 255
+}
+__device__ __forceinline__ uint8_t depth_to_u8(float depth, float d_near, float d_range) {
+    const float x = __fdiv_rn(__fsub_rn(depth, d_near), d_range);                              // render_video.py:123
+    return (uint8_t)(int)__fmul_rn(fminf(fmaxf(x, 0.0f), 1.0f), 255.0f);                         // clip, * 255, astype(uint8)
+}
+
 // Store one finished pixel: plain outputs, or the same frame slot of every rank's gather buffer (NVLink peer stores).
+__device__ __forceinline__ uint8_t color_to_u8(float img_m11, bool round_half_up);
+__device__ __forceinline__ uint8_t depth_to_u8(float depth, float d_near, float d_range);
 __device__ __forceinline__ void store_pixel(const RenderParams& p, int v, size_t img, size_t pix, float c0, float c1, float c2, float dep) {
-    if (p.n_peers > 0) {
+    if (p.video_rgb) {        // uint8 HWC frame (render_video.py:118-126)
+        const bool up = (p.options & GMPI_U8_ROUND_HALF_UP) != 0;
+        uint8_t* c = p.video_rgb + ((size_t)v * img + pix) * 3;
+        c[0] = color_to_u8(c0, up); c[1] = color_to_u8(c1, up); c[2] = color_to_u8(c2, up);
+        if (p.video_depth) p.video_depth[(size_t)v * img + pix] = depth_to_u8(dep, p.depth_near, p.depth_range);
+    } else if (p.n_peers > 0) {
         const size_t fo = (size_t)(p.frame_offset + v) * 4 * img + pix;
         for (int r = 0; r < p.n_peers; ++r) {
             float* f = p.peer_frames[r] + fo;

@@ -43,13 +43,14 @@ constexpr int kMaxPlanesStaged = GMPI_MAX_PLANES_STAGED;   // plane-constant tab
 constexpr int kCtasPerSm = GMPI_CTAS_PER_SM;
 constexpr int kStageFloats = kMaxBW * kMaxBH * 4;
 constexpr size_t kStagedSmem = (size_t)kStages * kStageFloats * 4 + (size_t)kMaxPlanesStaged * 32;
-constexpr size_t kStagedSmemBwd = (size_t)kStages * (kStageFloats + kTileW * kTileH) * 4 + (size_t)kMaxPlanesStaged * 32;
 
 struct TmaMaps {
-    CUtensorMap m[kNumMaps];
-    CUtensorMap t;      // backward only: saved transmittance [V*N][H][W], box {kTileW, kTileH, 1}
+    CUtensorMap m[kNumMaps];      // expanded rgba [M*N][4][Ht][Wt] as (x, channel, y, plane), box {bw, 4, 4 rows, 1}
+    // factored MPI: shared colour [M][3][Ht][Wt] as (x, channel, y, mpi), box {bw, 3, 4 rows, 1}; the last plane's own colour
+    // (torgba_sep_background) likewise; per-plane alpha [M*N][Ht][Wt] as (x, y, plane), box {bw, 4 rows, 1}
+    CUtensorMap rgb[kNumMaps], bg[kNumMaps], a[kNumMaps];
+    CUtensorMap t;      // backward only: saved transmittance [V*N][H][W], box {64, 24, 1} (the backward's tile)
 };
-constexpr int kStageFloatsBwd = kStageFloats + kTileW * kTileH;   // backward stages also carry the tile's transmittance
 
 // per-stage header written by the producer before it arms the full barrier
 struct __align__(16) StageMeta {
@@ -146,12 +147,17 @@ __device__ __forceinline__ void coords_pairs(const PlaneConst& pc, const RayPair
 
 // Sample + composite the four pixels from a staged box of compile-time width BW.  Returns false (and changes nothing)
 // if any of the four footprints is not inside the box.
-template <int BW>
+// AOFF == 0: expanded stage [row][4 channels][BW].  AOFF > 0 (factored MPI): colour box [row][3][BW] at the stage base and
+// the alpha box [row][BW] AOFF floats further on.
+template <int BW, int AOFF = 0>
 __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, int cx, int cy, int rows2, const CoordPairs& c,
                                              f2 (&T)[kPairs], f2 (&cr)[kPairs], f2 (&cg)[kPairs], f2 (&cb)[kPairs], f2 (&cws)[kPairs]) {
+    constexpr int RP = AOFF ? 3 * BW : 4 * BW;       // colour row pitch
+    constexpr int AP = AOFF ? BW : 4 * BW;           // alpha row pitch
+    constexpr int A0 = AOFF ? AOFF : 3 * BW;         // alpha offset from the colour index (factored: separate box)
     const f2 m1 = splat(-1.0f), one = splat(1.0f);
     f2 fx0[kPairs], fy0[kPairs];
-    int ia[kPairs], ib[kPairs];
+    int ia[kPairs], ib[kPairs], ja[kPairs], jb[kPairs];
     bool inbox = true;
     const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
 #pragma unroll
@@ -163,8 +169,9 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, int c
         const int rya = __float_as_int(ty.x) - cy, ryb = __float_as_int(ty.y) - cy;
         inbox = inbox && (unsigned)rxa <= (unsigned)(BW - 2) && (unsigned)rxb <= (unsigned)(BW - 2) &&
                 (unsigned)rya <= (unsigned)rows2 && (unsigned)ryb <= (unsigned)rows2;
-        ia[P] = rya * (4 * BW) + rxa;                                 // [row][channel][x], compile-time pitch
-        ib[P] = ryb * (4 * BW) + rxb;
+        ia[P] = rya * RP + rxa;                                       // [row][channel][x], compile-time pitch
+        ib[P] = ryb * RP + rxb;
+        if (AOFF) { ja[P] = rya * AP + rxa + A0; jb[P] = ryb * AP + rxb + A0; }   // alpha taps (separate box)
     }
     if (!__all_sync(0xffffffffu, inbox)) return false;   // warp-uniform, so the caller's fallback needs no reconvergence scaffolding
 #pragma unroll
@@ -175,10 +182,19 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, int c
         const float* ta = sb + ia[P];
         const float* tb = sb + ib[P];
 #define GMPI_TAP(ch)                                                                                           \
-    fma2(make_float2(ta[(4 + ch) * BW + 1], tb[(4 + ch) * BW + 1]), w11,                                       \
-         fma2(make_float2(ta[(4 + ch) * BW], tb[(4 + ch) * BW]), w10,                                          \
+    fma2(make_float2(ta[RP + ch * BW + 1], tb[RP + ch * BW + 1]), w11,                                         \
+         fma2(make_float2(ta[RP + ch * BW], tb[RP + ch * BW]), w10,                                            \
               fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
-        const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2), a = GMPI_TAP(3);
+        const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2);
+        f2 a;
+        if (AOFF == 0) {
+            a = GMPI_TAP(3);
+        } else {
+            const float* aa = sb + ja[P];
+            const float* ab = sb + jb[P];
+            a = fma2(make_float2(aa[AP + 1], ab[AP + 1]), w11,
+                     fma2(make_float2(aa[AP], ab[AP]), w10, fma2(make_float2(aa[1], ab[1]), w01, mul2(make_float2(aa[0], ab[0]), w00))));
+        }
 #undef GMPI_TAP
         const f2 w = mul2(a, T[P]);                     // mpi.py:423
         cr[P] = fma2(w, r, cr[P]);                      // mpi.py:430
@@ -192,10 +208,9 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, int c
 
 // Rare path (a ray whose footprint is not in the staged box): sample the plane from global memory.  Out of line so
 // that it does not cost registers in the hot loop.
-__device__ __noinline__ float4 sample_plane_direct(const float* __restrict__ plane, int Ht, int Wt, float ix, float iy) {
-    const size_t tex = (size_t)Ht * Wt;
+__device__ __noinline__ float4 sample_plane_direct(const PlaneChans pl, int Ht, int Wt, float ix, float iy) {
     const Taps tp = make_taps(ix, iy, Ht, Wt);
-    return make_float4(tap4(plane, tp), tap4(plane + tex, tp), tap4(plane + 2 * tex, tp), tap4(plane + 3 * tex, tp));
+    return make_float4(tap4(pl.c[0], tp), tap4(pl.c[1], tp), tap4(pl.c[2], tp), tap4(pl.c[3], tp));
 }
 
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
@@ -210,34 +225,47 @@ struct TileWalk {
     int tiles_x, full_rows, full_per_view, n_full, n_part;
     int cta, grid;               // blockIdx.x, gridDim.x (members so that the host-side test hook runs the same code)
     int n1, p_start, p_step;     // this CTA: number of full tiles; first partial tile and stride (p_step == 0: none)
+    int tile_h;                  // tile height in pixels (forward: kTileH = 30, backward: 24)
+    int group;                   // views per MPI when consecutive views share one (1: order tiles view by view).  With
+                                 // group > 1 the views of a group are the FASTEST index: the CTAs running at the same time
+                                 // work on the same tile position of different views of one MPI, i.e. on (nearly) the same
+                                 // texels, which then come from L2 instead of HBM (video render: 120 views of one MPI)
     // (lives in shared memory, filled by one thread: it is read once per tile and must not cost registers in the plane loop)
-    __host__ __device__ __forceinline__ void init(int tiles_x_, int H, int V, int cta_, int grid_) {
+    __host__ __device__ __forceinline__ void init(int tiles_x_, int H, int V, int cta_, int grid_, int tile_h_ = kTileH, int group_ = 1) {
         tiles_x = tiles_x_;
         cta = cta_; grid = grid_;
-        full_rows = H / kTileH;
+        tile_h = tile_h_;
+        group = (group_ > 1 && V % group_ == 0) ? group_ : 1;
+        full_rows = H / tile_h;
         full_per_view = tiles_x * full_rows;
         n_full = full_per_view * V;
-        n_part = (H % kTileH) ? tiles_x * V : 0;
+        n_part = (H % tile_h) ? tiles_x * V : 0;
         const int b = cta, G = grid, r = n_full % G;
         n1 = b < n_full ? (n_full - b + G - 1) / G : 0;
         if (r == 0) { p_start = b; p_step = G; }
         else if (b >= r) { p_start = b - r; p_step = G - r; }
         else { p_start = 0; p_step = 0; }
     }
+    // index t of a sequence of `per_view` positions x V views -> (view, position): view-major, or group-minor
+    __host__ __device__ __forceinline__ void split(int t, int per_view, int& v, int& pos) const {
+        if (group == 1) { v = t / per_view; pos = t - v * per_view; return; }
+        const int per_group = per_view * group, g = t / per_group, rem = t - g * per_group;
+        pos = rem / group;
+        v = g * group + (rem - pos * group);
+    }
     // j-th tile of this CTA; false when done
     __host__ __device__ __forceinline__ bool at(int j, TileXY& r) const {
+        int pos;
         if (j < n1) {
-            const int t = cta + j * grid;
-            r.v = t / full_per_view;
-            const int tt = t - r.v * full_per_view;
-            r.px0 = (tt % tiles_x) * kTileW; r.py0 = (tt / tiles_x) * kTileH;
+            split(cta + j * grid, full_per_view, r.v, pos);
+            r.px0 = (pos % tiles_x) * kTileW; r.py0 = (pos / tiles_x) * tile_h;
             return true;
         }
         if (p_step == 0) return false;
         const int u = p_start + (j - n1) * p_step;
         if (u >= n_part) return false;
-        r.v = u / tiles_x;
-        r.px0 = (u - r.v * tiles_x) * kTileW; r.py0 = full_rows * kTileH;
+        split(u, tiles_x, r.v, pos);
+        r.px0 = pos * kTileW; r.py0 = full_rows * tile_h;
         return true;
     }
 };
@@ -257,30 +285,45 @@ __device__ __forceinline__ void consumer_idle_tile(uint64_t* s_full, uint64_t* s
 // Producer warp, shared by the forward (front-to-back) and backward (back-to-front) kernels: for every (tile, plane) of
 // this CTA, estimate the tile's texel footprint from its four corner rays, pick the narrowest box class, publish the stage
 // header and issue the TMA copies.
-template <bool kAlignCorners, bool kReverse>
+// Ring geometry of a kernel: tile height, ring depth, the largest staged box and what a stage holds.
+struct FwdRing {
+    static constexpr int kTileRows = kTileH, kRingStages = kStages, kBoxMaxH = kMaxBH;
+    static constexpr int kPlaneFloats = kStageFloats;      // floats of one staged plane box
+    static constexpr int kStride = kStageFloats;           // floats per ring stage
+    static constexpr bool kReverse = false;                // planes front to back; no transmittance box
+};
+// factored MPI: the colour box [row][3][bw] starts the stage, the alpha box [row][bw] follows at this offset (floats)
+constexpr int kFwdAlphaOff = 3 * kMaxBW * kMaxBH;
+
+template <bool kAlignCorners, class Ring>
 __device__ __forceinline__ void staged_producer(const RenderParams& p, const TmaMaps& maps, float* s_buf, StageMeta* s_meta,
                                             uint64_t* s_full, uint64_t* s_empty, const TileWalk* s_walk, int lane) {
-    constexpr int kStride = kReverse ? kStageFloatsBwd : kStageFloats;      // floats per ring stage
+    constexpr bool kReverse = Ring::kReverse;
+    constexpr int kStride = Ring::kStride;      // floats per ring stage
+    constexpr int kTileH = Ring::kTileRows, kStages = Ring::kRingStages, kMaxBH = Ring::kBoxMaxH, kStageFloats = Ring::kPlaneFloats;
     constexpr uint32_t kTBytes = kReverse ? (uint32_t)(kTileW * kTileH * 4) : 0u;
     const int Ht = p.Ht, Wt = p.Wt, N = p.N;
     const float fWt = (float)Wt, fHt = (float)Ht;
     const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
     const size_t img = (size_t)p.H * p.W;
-    if (lane < kNumMaps) tma_prefetch_desc(&maps.m[lane]);
+    if (lane < kNumMaps) {
+        if (p.alpha) { tma_prefetch_desc(&maps.rgb[lane]); tma_prefetch_desc(&maps.a[lane]); }
+        else tma_prefetch_desc(&maps.m[lane]);
+    }
     int p_stage = 0;
     uint32_t p_phase = 0;
     TileXY txy;
     for (int j = 0; s_walk->at(j, txy); ++j) {
         const int v = txy.v, px0 = txy.px0, py0 = txy.py0;
         const int m = __ldg(p.view2mpi + v);
-        const float* e = p.eye + 3 * v;
-        const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
-        const float zd[3] = {0.f, 0.f, 1.f};
+        float ev[3], zd[3];
+        load_eye_z(p, v, ev, zd);
         // the four corner pixels of the tile (replicated over the warp), clamped into the image
         const int cx = min(px0 + ((lane & 1) ? kTileW - 1 : 0), p.W - 1);
         const int cy = min(py0 + ((lane & 2) ? kTileH - 1 : 0), p.H - 1);
-        const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)cy * p.W + cx;
-        const RayConst rc = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+        float crx, cry, crz;
+        load_ray(p, v, cx, cy, img, crx, cry, crz);
+        const RayConst rc = make_ray_const(crx, cry, crz, ev, zd);
         for (int ii = 0; ii < N; ++ii) {
             const int i = kReverse ? N - 1 - ii : ii;
             const int s = p_stage;
@@ -319,14 +362,72 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             }
             __syncwarp();
             if (lane < n_ops) {
-                float* dst = s_buf + (size_t)s * kStride + (size_t)lane * kRowsPerOp * 4 * bw;
-                tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
+                if (p.alpha) {       // factored MPI: shared colour (or the last plane's own) + this plane's alpha, two boxes
+                    float* stage = s_buf + (size_t)s * kStride;
+                    const CUtensorMap* cmap = (p.bg_rgb && i == N - 1) ? &maps.bg[k] : &maps.rgb[k];
+                    tma_load_4d(stage + (size_t)lane * kRowsPerOp * 3 * bw, cmap, &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m);
+                    tma_load_3d(stage + (kStageFloats / 4) * 3 + (size_t)lane * kRowsPerOp * bw, &maps.a[k], &s_full[s], bx0,
+                                by0 + lane * kRowsPerOp, m * N + i);
+                } else {
+                    float* dst = s_buf + (size_t)s * kStride + (size_t)lane * kRowsPerOp * 4 * bw;
+                    tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
+                }
             }
         }
     }
 }
 
-template <bool kAlignCorners, bool kEmitT>
+// 4x4 transpose inside every quad of lanes (4 q .. 4 q + 3): on entry lane k of a quad holds a[c] = M[k][c], on return
+// a[t] = M[t][k].  Two butterfly steps, four shuffles.
+__device__ __forceinline__ void quad_transpose(float (&a)[4], int lane) {
+    const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+    {   // exchange 2x2 blocks with lane ^ 2
+        const float s0 = hi2 ? a[0] : a[2], s1 = hi2 ? a[1] : a[3];
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+        if (hi2) { a[0] = r0; a[1] = r1; } else { a[2] = r0; a[3] = r1; }
+    }
+    {   // exchange inside the 2x2 blocks with lane ^ 1
+        const float s0 = hi1 ? a[0] : a[1], s1 = hi1 ? a[2] : a[3];
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+        if (hi1) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
+    }
+}
+
+// Epilogue of one consumer warp: rows py, py + 1 of the tile, 64 pixels each; out[q] = (R, G, B, depth) of pixel
+// (px0 + lane + 32 (q & 1), py + (q >> 1)).  Three destinations:
+//   * uint8 video frames (HWC colour + normalised depth, render_video.py:118-126) when video_rgb is set;
+//   * float4 stores after a quad transpose (lane k of a quad ends up with channel k of four consecutive x): 4 x STG.128 per
+//     thread instead of 16 x STG.32 -- and 4 per peer in the fused all-gather, or 4 in total through a multicast address;
+//   * the scalar store_pixel path for odd widths / unaligned outputs.
+__device__ __forceinline__ void store_tile_rows(const RenderParams& p, int v, size_t img, int px0, int py, int lane, float (&out)[kPix][4]) {
+    if (p.options & kOptVec4Stores) {
+        const int k = lane & 3, xq = 4 * (lane >> 2);
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) {
+            quad_transpose(out[q], lane);          // all lanes take part, whatever their bounds
+            const int px = px0 + 32 * (q & 1) + xq, pyq = py + (q >> 1);
+            if (px >= p.W || pyq >= p.H) continue;  // W % 4 == 0: a quad is inside or outside as a whole
+            const float4 val = make_float4(out[q][0], out[q][1], out[q][2], out[q][3]);
+            const size_t pix = (size_t)pyq * p.W + px;
+            if (p.n_peers > 0) {
+                const size_t fo = ((size_t)(p.frame_offset + v) * 4 + k) * img + pix;
+                for (int r = 0; r < p.n_peers; ++r) *reinterpret_cast<float4*>(p.peer_frames[r] + fo) = val;
+            } else {
+                float* dst = k < 3 ? p.color + ((size_t)v * 3 + k) * img + pix : p.depth + (size_t)v * img + pix;
+                *reinterpret_cast<float4*>(dst) = val;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) {
+        const int px = px0 + lane + 32 * (q & 1), pyq = py + (q >> 1);
+        if (px >= p.W || pyq >= p.H) continue;
+        store_pixel(p, v, img, (size_t)pyq * p.W + px, out[q][0], out[q][1], out[q][2], out[q][3]);
+    }
+}
+
+template <bool kAlignCorners, bool kEmitT, bool kFactored>
 __global__ void __launch_bounds__(kStagedThreads, kCtasPerSm)
 mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -338,7 +439,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        s_walk.init(tiles_x, p.H, p.V, (int)blockIdx.x, (int)gridDim.x);
+        s_walk.init(tiles_x, p.H, p.V, (int)blockIdx.x, (int)gridDim.x, kTileH, p.view_group);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], kConsWarps);
@@ -353,7 +454,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const size_t img = (size_t)p.H * p.W;
 
     if (warp == kConsWarps) {
-        staged_producer<kAlignCorners, false>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
+        staged_producer<kAlignCorners, FwdRing>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
     } else {
         // ================================ consumer warps ================================
         // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them
@@ -373,9 +474,8 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
         for (int j = 0; s_walk.at(j, txy); ++j) {
             const int v = txy.v, px0 = txy.px0, py0 = txy.py0;
             const int m = __ldg(p.view2mpi + v);
-            const float* e = p.eye + 3 * v;
-            const float ev[3] = {__ldg(e), __ldg(e + 1), __ldg(e + 2)};
-            const float zd[3] = {__ldg(p.z_dir + 3 * v), __ldg(p.z_dir + 3 * v + 1), __ldg(p.z_dir + 3 * v + 2)};
+            float ev[3], zd[3];
+            load_eye_z(p, v, ev, zd);
             if (v != v_table) {          // (view, plane) constants, once per view and CTA
                 consumer_bar_sync();     // everyone is done with the previous view's table
                 for (int i = threadIdx.x; i < N; i += kConsThreads) s_pc[i] = make_plane_const(p.dhw + ((size_t)m * N + i) * 3, ev[2]);
@@ -386,15 +486,15 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 consumer_idle_tile(s_full, s_empty, N, lane, c_stage, c_phase);
                 continue;
             }
-            const float* rays = p.ray_dir + (size_t)v * 3 * img;
             RayConst rc[kPix];   // scalar copies, only for the generic (rare) body and the epilogue
             RayPairs rp;
             bool rays_fast = (in_safe_range(ev[0]) || ev[0] == 0.0f) && (in_safe_range(ev[1]) || ev[1] == 0.0f);
 #pragma unroll
             for (int q = 0; q < kPix; ++q) {
                 const int px = min(px0 + lane + 32 * (q & 1), p.W - 1), py = min(py0 + kPairs * warp + (q >> 1), p.H - 1);
-                const float* rd = rays + (size_t)py * p.W + px;
-                rc[q] = make_ray_const(__ldg(rd), __ldg(rd + img), __ldg(rd + 2 * img), ev, zd);
+                float qx, qy, qz;
+                load_ray(p, v, px, py, img, qx, qy, qz);
+                rc[q] = make_ray_const(qx, qy, qz, ev, zd);
                 rays_fast = rays_fast && rc[q].fast && fabsf(rc[q].rx2) <= 0x1p40f && fabsf(rc[q].ry2) <= 0x1p40f;
             }
 #pragma unroll
@@ -436,18 +536,18 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 const int sel = mt.sel;                  // warp-uniform; the producer already folded mode and plane range in
                 bool done = false;
                 if (warp_fast) {                         // most frequent classes first (FFHQ poses: 72 > 64 > 80 >> 56, 88)
-                    if (sel & (1 << 18)) done = sample_pairs<72>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 17)) done = sample_pairs<64>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 19)) done = sample_pairs<80>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 16)) done = sample_pairs<56>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 20)) done = sample_pairs<88>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    if (sel & (1 << 18)) done = sample_pairs<72, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 17)) done = sample_pairs<64, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 19)) done = sample_pairs<80, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 16)) done = sample_pairs<56, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    else if (sel & (1 << 20)) done = sample_pairs<88, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
                 }
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----
                     const int bw = mt.sel & 0xff, mode = (mt.sel >> 8) & 3, bw4 = 4 * bw;
                     const float fbw2 = (float)(bw - 2), fbh2 = (float)mt.rows2;
                     const float fbx0 = (float)(mt.cx - kFloorMagicBits), fby0 = (float)(mt.cy - kFloorMagicBits);
-                    const float* plane = p.rgba + ((size_t)m * N + i) * 4 * tex;
+                    const PlaneChans plane = plane_chans(p, m, i, tex);
                     float* Ts = reinterpret_cast<float*>(T);
                     float* crs = reinterpret_cast<float*>(cr);
                     float* cgs = reinterpret_cast<float*>(cg);
@@ -461,7 +561,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);
                         const float rxx = fx - fbx0, ryy = fy - fby0;
                         float r, g, b, a;
-                        if (mode == 0 && rxx >= 0.0f && rxx <= fbw2 && ryy >= 0.0f && ryy <= fbh2) {
+                        if (!kFactored && mode == 0 && rxx >= 0.0f && rxx <= fbw2 && ryy >= 0.0f && ryy <= fbh2) {
                             const float wx1 = tc.ix - fx, wy1 = tc.iy - fy;
                             const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
                             const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
@@ -499,19 +599,19 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
                 }
             }
+            // ---- epilogue: the warp's 2 rows x 64 pixels, (R, G, B, depth) per pixel ----
+            float out[kPix][4];
 #pragma unroll
             for (int q = 0; q < kPix; ++q) {
-                const int px = px0 + lane + 32 * (q & 1), py = py0 + kPairs * warp + (q >> 1);
-                if (px >= p.W || py >= p.H) continue;
-                const size_t pix = (size_t)py * p.W + px;
                 float o0 = (q & 1) ? cr[q >> 1].y : cr[q >> 1].x, o1 = (q & 1) ? cg[q >> 1].y : cg[q >> 1].x;
                 float o2 = (q & 1) ? cb[q >> 1].y : cb[q >> 1].x;
                 const float ws = (q & 1) ? cws[q >> 1].y : cws[q >> 1].x;
                 if (minus1_1) {
                     o0 = fmaf(2.0f, o0, -1.0f); o1 = fmaf(2.0f, o1, -1.0f); o2 = fmaf(2.0f, o2, -1.0f);
                 }
-                store_pixel(p, v, img, pix, o0, o1, o2, ws * rc[q].dz);
+                out[q][0] = o0; out[q][1] = o1; out[q][2] = o2; out[q][3] = ws * rc[q].dz;
             }
+            store_tile_rows(p, v, img, px0, py0 + kPairs * warp, lane, out);
         }
         if (flag) atomicOr(p.flags, flag);
     }

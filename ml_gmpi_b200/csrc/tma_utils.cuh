@@ -107,4 +107,18 @@ inline int encode_plane_map(CUtensorMap* out, const float* base, uint64_t n_plan
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Tensor map over a shared colour image rgb [M][3 ch][Ht][Wt] (factored MPI) with the dimensions ordered (x, channel, y, mpi):
+// a box {bw, 3, rows, 1} lands in shared memory as [row][channel][x].
+inline int encode_color_map(CUtensorMap* out, const float* base, uint64_t n_mpi, int Ht, int Wt, int bw, int rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[4] = {(cuuint64_t)Wt, 3, (cuuint64_t)Ht, (cuuint64_t)n_mpi};
+    cuuint64_t strides[3] = {(cuuint64_t)Wt * Ht * 4, (cuuint64_t)Wt * 4, (cuuint64_t)Wt * Ht * 12};
+    cuuint32_t box[4] = {(cuuint32_t)bw, 3, (cuuint32_t)rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 }  // namespace gmpi

@@ -32,97 +32,179 @@ def _as_f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 class _RenderFn(torch.autograd.Function):
+    """MPI.forward + its autograd through the C ABI's descriptor entry points (gmpi_mpi_render_fwd_ex / _bwd_ex).
+    The MPI is either expanded (`rgba`) or factored (`rgb`, `alpha`, optional `bg_rgb`); the unused form is None."""
+
     @staticmethod
-    def forward(ctx, rgba, dhw, view2mpi, ray_dir, eye, z_dir, options, flags):
+    def forward(ctx, rgba, rgb, alpha, bg_rgb, dhw, view2mpi, ray_dir, eye, z_dir, options, flags, view_group):
         lib = _lib.load()
-        M, N, _, Ht, Wt = rgba.shape
+        factored = rgba is None
+        ref = alpha if factored else rgba
+        M, N = ref.shape[0], ref.shape[1]
+        Ht, Wt = ref.shape[-2:]
         V, _, H, W = ray_dir.shape
-        color = torch.empty((V, 3, H, W), device=rgba.device, dtype=torch.float32)
-        depth = torch.empty((V, 1, H, W), device=rgba.device, dtype=torch.float32)
+        dev = ref.device
+        color = torch.empty((V, 3, H, W), device=dev, dtype=torch.float32)
+        depth = torch.empty((V, 1, H, W), device=dev, dtype=torch.float32)
         # training: the forward also saves the transmittance in front of every plane (4 B per pixel-plane) so that the
         # backward is ONE staged back-to-front sweep (torch autograd keeps ~30 such tensors alive for the reference)
         trans = None
-        if ctx.needs_input_grad[0]:
-            trans = torch.empty((V, N, H, W), device=rgba.device, dtype=torch.float32)
-        with torch.cuda.device(rgba.device):
-            if trans is not None:
-                _lib.check(lib.gmpi_mpi_render_fwd_train(
-                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
-                    color.data_ptr(), depth.data_ptr(), trans.data_ptr(), flags.data_ptr(),
-                    M, V, N, Ht, Wt, H, W, options, _stream_ptr(rgba.device)))
-            else:
-                _lib.check(lib.gmpi_mpi_render_fwd(
-                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(),
-                    z_dir.data_ptr(), color.data_ptr(), depth.data_ptr(), flags.data_ptr(),
-                    M, V, N, Ht, Wt, H, W, options, _stream_ptr(rgba.device)))
-        ctx.save_for_backward(rgba, dhw, view2mpi, ray_dir, eye, z_dir, trans)
-        ctx.options = options
+        if any(ctx.needs_input_grad[:4]):
+            trans = torch.empty((V, N, H, W), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            d = _lib.make_desc(options=options, M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W, view_group=view_group, rgba=rgba, rgb=rgb,
+                               alpha=alpha, bg_rgb=bg_rgb, view2mpi=view2mpi, dhw=dhw, ray_dir=ray_dir, eye=eye, z_dir=z_dir,
+                               color=color, depth=depth, transmittance=trans, flags=flags, stream=_stream_ptr(dev))
+            _lib.check(lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)))
+        ctx.save_for_backward(rgba, rgb, alpha, bg_rgb, dhw, view2mpi, ray_dir, eye, z_dir, trans)
+        ctx.options, ctx.view_group = options, view_group
         ctx.set_materialize_grads(False)
         return color, depth
 
     @staticmethod
     @torch.autograd.function.once_differentiable     # raw kernels: a double backward (create_graph=True) must raise, not
-    def backward(ctx, g_color, g_depth):             # silently treat g_rgba as constant (the reference's R1 only differentiates D)
-        rgba, dhw, view2mpi, ray_dir, eye, z_dir, trans = ctx.saved_tensors
-        if not ctx.needs_input_grad[0]:
-            return (None,) * 8
+    def backward(ctx, g_color, g_depth):             # silently treat the result as constant (the reference's R1 only differentiates D)
+        rgba, rgb, alpha, bg_rgb, dhw, view2mpi, ray_dir, eye, z_dir, trans = ctx.saved_tensors
+        none = (None,) * 12
+        if not any(ctx.needs_input_grad[:4]):
+            return none
         lib = _lib.load()
-        M, N, _, Ht, Wt = rgba.shape
+        factored = rgba is None
+        ref = alpha if factored else rgba
+        M, N = ref.shape[0], ref.shape[1]
+        Ht, Wt = ref.shape[-2:]
         V, _, H, W = ray_dir.shape
+        dev = ref.device
         if g_color is None:
-            g_color = torch.zeros((V, 3, H, W), device=rgba.device, dtype=torch.float32)
+            g_color = torch.zeros((V, 3, H, W), device=dev, dtype=torch.float32)
         g_color = _as_f32c(g_color)
-        gd_ptr = None
-        if g_depth is not None:
-            g_depth = _as_f32c(g_depth)
-            gd_ptr = g_depth.data_ptr()
-        g_rgba = torch.empty_like(rgba)
-        with torch.cuda.device(rgba.device):   # autograd worker threads do not inherit the device
-            if trans is not None:
-                _lib.check(lib.gmpi_mpi_render_bwd_saved(
-                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
-                    trans.data_ptr(), g_color.data_ptr(), gd_ptr, g_rgba.data_ptr(),
-                    M, V, N, Ht, Wt, H, W, ctx.options | _lib.OPT_ZERO_GRAD, _stream_ptr(rgba.device)))
-            else:
-                _lib.check(lib.gmpi_mpi_render_bwd(
-                    rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(),
-                    z_dir.data_ptr(), g_color.data_ptr(), gd_ptr, g_rgba.data_ptr(),
-                    M, V, N, Ht, Wt, H, W, ctx.options | _lib.OPT_ZERO_GRAD, _stream_ptr(rgba.device)))
-        return g_rgba, None, None, None, None, None, None, None
+        g_depth = _as_f32c(g_depth) if g_depth is not None else None
+        g_rgba = g_rgb = g_alpha = g_bg = None
+        if factored:
+            g_rgb, g_alpha = torch.empty_like(rgb), torch.empty_like(alpha)
+            g_bg = torch.empty_like(bg_rgb) if bg_rgb is not None else None
+        else:
+            g_rgba = torch.empty_like(rgba)
+        with torch.cuda.device(dev):   # autograd worker threads do not inherit the device
+            d = _lib.make_desc(options=ctx.options | _lib.OPT_ZERO_GRAD, M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W,
+                               view_group=ctx.view_group, rgba=rgba, rgb=rgb, alpha=alpha, bg_rgb=bg_rgb, view2mpi=view2mpi, dhw=dhw,
+                               ray_dir=ray_dir, eye=eye, z_dir=z_dir, transmittance=trans, g_color=g_color, g_depth=g_depth,
+                               g_rgba=g_rgba, g_rgb=g_rgb, g_bg_rgb=g_bg, g_alpha=g_alpha, stream=_stream_ptr(dev))
+            _lib.check(lib.gmpi_mpi_render_bwd_ex(ctypes.byref(d)))
+        return (g_rgba, g_rgb, g_alpha, g_bg) + (None,) * 8
 
 
 _warned_direct = set()
 
 
-def _warn_if_direct(rgba, V, H, W):
+def _warn_if_direct(ref, V, H, W):
     """Surface the direct-kernel performance cliff (several times slower than the TMA-staged kernels) once per shape."""
-    M, N, _, Ht, Wt = rgba.shape
-    key = (V, N, Ht, Wt, H, W, rgba.data_ptr() & 15)
+    N, (Ht, Wt) = ref.shape[1], ref.shape[-2:]
+    key = (V, N, Ht, Wt, H, W, ref.data_ptr() & 15)
     if key in _warned_direct:
         return
     _warned_direct.add(key)
     why = ctypes.c_uint32(0)
-    if _lib.load().gmpi_mpi_render_fwd_plan(V, N, Ht, Wt, H, W, rgba.data_ptr(), ctypes.byref(why)) == _lib.PLAN_DIRECT \
+    if _lib.load().gmpi_mpi_render_fwd_plan(V, N, Ht, Wt, H, W, ref.data_ptr(), ctypes.byref(why)) == _lib.PLAN_DIRECT \
             and (why.value & ~2 or V * N * H * W >= 1 << 26):      # "few tiles" only matters when the problem is not tiny
         reasons = "; ".join(t for b, t in _lib.WHY.items() if why.value & b)
         warnings.warn(f"ml_gmpi_b200: rendering V={V} N={N} tex={Ht}x{Wt} img={H}x{W} with the direct (one thread per pixel) "
                       f"kernels, several times slower than the TMA-staged path: {reasons}", RuntimeWarning, stacklevel=3)
 
 
+def _options(align_corners, check_last_plane, color_minus1_1, u8_round=False):
+    return (_lib.OPT_ALIGN_CORNERS if align_corners else 0) | (_lib.OPT_CHECK_LAST_PLANE if check_last_plane else 0) \
+        | (_lib.OPT_COLOR_MINUS1_1 if color_minus1_1 else 0) | (_lib.OPT_U8_ROUND_HALF_UP if u8_round else 0)
+
+
 def render_views(rgba, dhw, view2mpi, ray_dir, eye, z_dir, *, align_corners=True, check_last_plane=False,
-                 color_minus1_1=False, flags: Optional[torch.Tensor] = None):
+                 color_minus1_1=False, flags: Optional[torch.Tensor] = None, view_group: int = 1):
     """Functional form on packed tensors (no list handling, no host sync).
     rgba [M,N,4,Ht,Wt], dhw [M,N,3], view2mpi [V] int32, ray_dir [V,3,H,W], eye/z_dir [V,3].
-    Returns (color [V,3,H,W], depth [V,1,H,W]); `flags` (uint32 tensor of 1, int32 storage) is OR-ed into."""
+    Returns (color [V,3,H,W], depth [V,1,H,W]); `flags` (uint32 tensor of 1, int32 storage) is OR-ed into.
+    view_group > 1: every view_group consecutive views share one MPI (tile-order hint: L2 reuse, see the C header)."""
     if not rgba.is_cuda:
         raise RuntimeError("ml_gmpi_b200 renders on CUDA devices only (no CPU fallback); got a CPU tensor")
     if flags is None:
         flags = torch.zeros(1, dtype=torch.int32, device=rgba.device)
     _warn_if_direct(rgba, ray_dir.shape[0], ray_dir.shape[2], ray_dir.shape[3])
-    options = (_lib.OPT_ALIGN_CORNERS if align_corners else 0) | (_lib.OPT_CHECK_LAST_PLANE if check_last_plane else 0) \
-        | (_lib.OPT_COLOR_MINUS1_1 if color_minus1_1 else 0)
-    return _RenderFn.apply(_as_f32c(rgba), _as_f32c(dhw), view2mpi, _as_f32c(ray_dir), _as_f32c(eye), _as_f32c(z_dir),
-                           options, flags)
+    return _RenderFn.apply(_as_f32c(rgba), None, None, None, _as_f32c(dhw), view2mpi, _as_f32c(ray_dir), _as_f32c(eye), _as_f32c(z_dir),
+                           _options(align_corners, check_last_plane, color_minus1_1), flags, int(view_group))
+
+
+def render_views_factored(rgb, alpha, dhw, view2mpi, ray_dir, eye, z_dir, *, bg_rgb=None, align_corners=True,
+                          check_last_plane=False, color_minus1_1=False, flags: Optional[torch.Tensor] = None, view_group: int = 1):
+    """The same render from the generator's FACTORED output (networks_cond_on_pos_enc.py:950-975,984): one colour image
+    rgb [M,3,Ht,Wt] shared by all planes (bg_rgb [M,3,Ht,Wt]: the last plane's own colour under torgba_sep_background) and
+    alpha [M,N,1,Ht,Wt] -- what the reference expands to [M,N,4,Ht,Wt] (and copies per view, train.py:553-558,733-738) before
+    rendering.  Output identical to render_views on the expanded stack, 4x fewer HBM bytes; differentiable w.r.t. rgb, alpha
+    and bg_rgb (d/d rgb is the sum over the planes that share it)."""
+    if not alpha.is_cuda:
+        raise RuntimeError("ml_gmpi_b200 renders on CUDA devices only (no CPU fallback); got a CPU tensor")
+    assert rgb.ndim == 4 and rgb.shape[1] == 3 and alpha.ndim == 5 and alpha.shape[2] == 1 and rgb.shape[0] == alpha.shape[0] \
+        and rgb.shape[-2:] == alpha.shape[-2:], f"expected rgb [M,3,Ht,Wt] and alpha [M,N,1,Ht,Wt], got {rgb.shape}, {alpha.shape}"
+    assert bg_rgb is None or bg_rgb.shape == rgb.shape, f"bg_rgb must have rgb's shape, got {bg_rgb.shape}"
+    if flags is None:
+        flags = torch.zeros(1, dtype=torch.int32, device=alpha.device)
+    _warn_if_direct(alpha, ray_dir.shape[0], ray_dir.shape[2], ray_dir.shape[3])
+    return _RenderFn.apply(None, _as_f32c(rgb), _as_f32c(alpha), None if bg_rgb is None else _as_f32c(bg_rgb), _as_f32c(dhw), view2mpi,
+                           _as_f32c(ray_dir), _as_f32c(eye), _as_f32c(z_dir), _options(align_corners, check_last_plane, color_minus1_1),
+                           flags, int(view_group))
+
+
+def expand_factored(rgb, alpha, bg_rgb=None):
+    """[M,3,Ht,Wt] + [M,N,1,Ht,Wt] -> [M,N,4,Ht,Wt], the generator's expand + cat (networks_cond_on_pos_enc.py:950-975):
+    what the reference renders from; here only tests and callers that need the expanded stack use it."""
+    N = alpha.shape[1]
+    col = rgb.unsqueeze(1).expand(-1, N, -1, -1, -1)
+    if bg_rgb is not None:
+        col = torch.cat([col[:, : N - 1], bg_rgb.unsqueeze(1)], dim=1)
+    return torch.cat([col, alpha], dim=2).contiguous()
+
+
+def render_frames(*, dhw, view2mpi, rgba=None, rgb=None, alpha=None, bg_rgb=None, ray_dir=None, eye=None, z_dir=None, cam=None,
+                  align_corners=True, check_last_plane=False, video: Optional[dict] = None, u8_round=False,
+                  flags: Optional[torch.Tensor] = None, view_group: int = 1, H: Optional[int] = None, W: Optional[int] = None):
+    """Inference-only render with the opt-in fast paths of the C ABI (no autograd):
+      cam [V,16]     rays generated in the kernel from the pinhole camera (see camera.cam_params) instead of ray_dir/eye/z_dir;
+      video={"near": ray_start, "far": ray_end, "depth": True}   uint8 HWC frames as render_video.py:118-126 builds them:
+                     returns (rgb_u8 [V,H,W,3], depth_u8 [V,H,W,1] or None); otherwise (color in [-1,1], depth) fp32.
+    """
+    ref = alpha if rgba is None else rgba
+    if not ref.is_cuda:
+        raise RuntimeError("ml_gmpi_b200 renders on CUDA devices only (no CPU fallback); got a CPU tensor")
+    lib = _lib.load()
+    dev = ref.device
+    M, N = ref.shape[0], ref.shape[1]
+    Ht, Wt = ref.shape[-2:]
+    if cam is not None:
+        V = cam.shape[0]
+        assert H is not None and W is not None, "pass H and W with cam"
+        cam = _as_f32c(cam)
+    else:
+        V, _, H, W = ray_dir.shape
+        ray_dir, eye, z_dir = _as_f32c(ray_dir), _as_f32c(eye), _as_f32c(z_dir)
+    if flags is None:
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    color = depth = v_rgb = v_depth = None
+    near = rng = 0.0
+    if video is not None:
+        v_rgb = torch.empty((V, H, W, 3), device=dev, dtype=torch.uint8)
+        if video.get("depth", True):
+            v_depth = torch.empty((V, H, W, 1), device=dev, dtype=torch.uint8)
+        near = float(np.float32(video["near"]))
+        rng = float(np.float32(video["far"] - video["near"]))            # the python-double difference, rounded once (numpy weak scalar)
+    else:
+        color = torch.empty((V, 3, H, W), device=dev, dtype=torch.float32)
+        depth = torch.empty((V, 1, H, W), device=dev, dtype=torch.float32)
+    keep = [_as_f32c(t) if t is not None else None for t in (rgba, rgb, alpha, bg_rgb, dhw)]
+    with torch.cuda.device(dev):
+        d = _lib.make_desc(options=_options(align_corners, check_last_plane, True, u8_round), M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W,
+                           view_group=int(view_group), depth_near=near, depth_range=rng, rgba=keep[0], rgb=keep[1], alpha=keep[2],
+                           bg_rgb=keep[3], view2mpi=view2mpi, dhw=keep[4], ray_dir=ray_dir, eye=eye, z_dir=z_dir, cam=cam, color=color,
+                           depth=depth, video_rgb=v_rgb, video_depth=v_depth, flags=flags, stream=_stream_ptr(dev))
+        _lib.check(lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)))
+    return (v_rgb, v_depth) if video is not None else (color, depth)
 
 
 def check_range(rgba: torch.Tensor, flags: torch.Tensor) -> None:
@@ -187,6 +269,14 @@ class MPI(nn.Module):
         cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs, dim=0))
         return view2mpi, cat(list(batch_ray_dir)), cat(list(batch_eye_pos)), cat(list(batch_z_dir))
 
+    @staticmethod
+    def view_group_of(batch_ray_dir) -> int:
+        """k when every MPI is rendered from the same number k > 1 of views (the expand of train.py:733-738 /
+        train_helpers.py:181-186, a video sweep of one MPI): the kernels then order tiles for L2 reuse.  Else 1."""
+        counts = {int(r.shape[0]) for r in batch_ray_dir}
+        k = counts.pop() if len(counts) == 1 else 1
+        return k if k > 1 else 1
+
     def forward(self, *, batch_rgba: torch.Tensor, batch_dhw: torch.Tensor, batch_ray_dir: List[torch.Tensor],
                 batch_eye_pos: List[torch.Tensor], batch_z_dir: List[torch.Tensor],
                 separate_background: Union[None, torch.Tensor], assert_not_out_of_last_plane: bool = False,
@@ -204,7 +294,7 @@ class MPI(nn.Module):
         color, depth = render_views(rgba, batch_dhw.to(dev), view2mpi, ray_dir.to(dev), eye.to(dev), z_dir.to(dev),
                                     align_corners=self._align_corners,
                                     check_last_plane=bool(assert_not_out_of_last_plane) and self.validate != "off",
-                                    flags=flags)
+                                    flags=flags, view_group=self.view_group_of(batch_ray_dir))
         self._flags = flags
         self._flag_ctx = (batch_dhw, eye, c2w_mat, sphere_c)
         if self.validate == "full":

@@ -100,3 +100,32 @@ def test_plan_query_needs_no_gpu(lib):
     assert lib.gmpi_mpi_render_fwd_plan(1, 16, 64, 64, 48, 48, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 2
     assert lib.gmpi_mpi_render_fwd_plan(4, 600, 1024, 1024, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 4
     assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1024, 1024, 1024, 1024, 8, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 8
+
+
+def test_render_desc_matches_header():
+    """ctypes mirror of gmpi_render_desc: same fields, same order, pointer-sized where the header has pointers."""
+    hdr = open(os.path.join(ROOT, "include", "gmpi_mpi_render.h")).read()
+    body = re.search(r"typedef struct gmpi_render_desc \{(.*?)\} gmpi_render_desc;", hdr, re.S).group(1)
+    names = re.findall(r"\b([a-zA-Z_0-9]+)(?:,|;)", body)
+    assert [f[0] for f in _lib.RenderDesc._fields_] == names
+    d = _lib.make_desc(M=1, V=2, options=5)
+    assert d.struct_bytes == ctypes.sizeof(_lib.RenderDesc) and d.M == 1 and d.V == 2 and d.options == 5 and not d.rgba
+
+
+def test_descriptor_entry_points_validate_without_gpu(lib):
+    assert lib.gmpi_mpi_render_fwd_ex(None) == 1 and b"null descriptor" in lib.gmpi_last_error()
+    d = _lib.make_desc(M=1, V=1, N=1, Ht=4, Wt=4, H=4, W=4)
+    d.struct_bytes = 8
+    assert lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)) == 1 and b"struct_bytes" in lib.gmpi_last_error()
+    d = _lib.make_desc(M=1, V=1, N=1, Ht=4, Wt=4, H=4, W=4)
+    assert lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)) == 1 and b"null input" in lib.gmpi_last_error()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    # factored form needs both rgb and alpha; rgba and alpha together are rejected
+    d = _lib.make_desc(M=1, V=1, N=1, Ht=4, Wt=4, H=4, W=4, rgba=p, alpha=p, view2mpi=p, dhw=p, ray_dir=p, eye=p, z_dir=p)
+    assert lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)) == 1
+    # backward with cam is unsupported (fast mode is forward-only)
+    d = _lib.make_desc(M=1, V=1, N=1, Ht=4, Wt=4, H=4, W=4, rgba=p, view2mpi=p, dhw=p, cam=p, g_color=p, g_rgba=p)
+    assert lib.gmpi_mpi_render_bwd_ex(ctypes.byref(d)) == 3
+    d = _lib.make_desc(M=1, V=3, N=1, Ht=4, Wt=4, H=4, W=4, view_group=2, rgba=p, view2mpi=p, dhw=p, ray_dir=p, eye=p, z_dir=p)
+    assert lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)) == 1 and b"view_group" in lib.gmpi_last_error()

@@ -52,3 +52,40 @@ def test_rejects_bad_arguments():
     assert lib.gmpi_debug_tile_walk(0, 64, 1, 1, 0, None, 0) < 0
     assert lib.gmpi_debug_tile_walk(64, 64, 1, 4, 4, None, 0) < 0
     assert b"tile_walk" in lib.gmpi_last_error()
+
+
+def walk_ex(H, W, V, tile_h, group, grid, cta):
+    lib = _lib.load()
+    n = lib.gmpi_debug_tile_walk_ex(H, W, V, tile_h, group, grid, cta, None, 0)
+    assert n >= 0
+    out = np.zeros((max(n, 1), 3), dtype=np.int32)
+    assert lib.gmpi_debug_tile_walk_ex(H, W, V, tile_h, group, grid, cta, out.ctypes.data_as(ctypes.c_void_p), n) == n
+    return [tuple(int(x) for x in row) for row in out[:n]]
+
+
+@pytest.mark.parametrize("H,W,V,tile_h,group,grid", [
+    (512, 512, 120, 30, 120, 148),     # video render: 120 views of one MPI
+    (512, 512, 15, 30, 15, 148), (256, 256, 8, 30, 4, 148), (224, 224, 12, 30, 3, 37),
+    (1024, 1024, 4, 24, 1, 148), (512, 512, 4, 24, 1, 148), (200, 200, 6, 24, 2, 148),      # backward tiles (64 x 24)
+    (100, 70, 4, 24, 4, 5), (48, 64, 2, 24, 2, 2),
+])
+def test_grouped_walk_covers_every_tile_once(H, W, V, tile_h, group, grid):
+    tiles_x, tiles_y = -(-W // TILE_W), -(-H // tile_h)
+    expected = {(v, x * TILE_W, y * tile_h) for v in range(V) for x in range(tiles_x) for y in range(tiles_y)}
+    seen, first = [], []
+    for cta in range(grid):
+        t = walk_ex(H, W, V, tile_h, group, grid, cta)
+        part = [py0 + tile_h > H for (_, _, py0) in t]
+        assert part == sorted(part)
+        seen += t
+        if t:
+            first.append(t[0])
+    assert len(seen) == len(expected) and set(seen) == expected
+    if group > 1 and grid >= 2 * group and tiles_x * (H // tile_h) >= 2:
+        # the CTAs that start together work on the same tile position of the views of one group (L2 reuse)
+        pos0 = [(px, py) for (v, px, py) in first[:group]]
+        assert len(set(pos0)) == 1 and sorted(v for (v, _, _) in first[:group]) == list(range(group))
+
+
+def test_group_that_does_not_divide_v_falls_back_to_view_major():
+    assert walk_ex(256, 256, 7, 30, 4, 148, 0) == walk_ex(256, 256, 7, 30, 1, 148, 0)

@@ -12,6 +12,11 @@ for step in "$@"; do
     bench)  timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -c 600 $OUT/${TAG}_bench.err ;;
     ref)    timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_ref.json 2> $OUT/${TAG}_ref.err; echo "ref rc=$?" ;;
     probe)  timeout 120 ./tools/l2_reduce_probe > $OUT/${TAG}_l2probe.txt 2>&1; echo "probe rc=$?"; cat $OUT/${TAG}_l2probe.txt ;;
+    bwdtests) timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "backward or grad or non_projective" > $OUT/${TAG}_pytest_bwd.log 2>&1; echo "bwd pytest rc=$?"; tail -5 $OUT/${TAG}_pytest_bwd.log ;;
+    trainbench) timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-reference-on-gpu > $OUT/${TAG}_trainbench.json 2> $OUT/${TAG}_trainbench.err; echo "trainbench rc=$?"; python -c "import json;d=json.load(open('$OUT/${TAG}_trainbench.json'));print(d['value'],d['roofline']['frac'],d['train_step'],d['configs']['C5_train_512'])" ;;
+    ncubwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:mpi_bwd -c 1 -o $OUT/${TAG}_prof_bwd python tools/run_one.py bwd > $OUT/${TAG}_ncu_bwd.log 2>&1; echo "ncu bwd rc=$?" ;;
+    ncufwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:mpi_fwd_staged -c 1 -o $OUT/${TAG}_prof_fwd python tools/run_one.py fwd > $OUT/${TAG}_ncu_fwd.log 2>&1; echo "ncu fwd rc=$?" ;;
+    sanitize) timeout 900 compute-sanitizer --tool racecheck python tools/run_one.py small > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 $OUT/${TAG}_racecheck.log; timeout 900 compute-sanitizer --tool memcheck python tools/run_one.py small > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 $OUT/${TAG}_memcheck.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
