@@ -210,6 +210,29 @@ int gmpi_mpi_render_bwd_ex(const gmpi_render_desc* desc);
 int gmpi_mpi_render_host_ex(const gmpi_render_desc* desc, int device);
 
 /*
+ * LightRenderer (gmpi/core/light_renderer.py), the lighting augmentation applied to the MPI right before the render call in
+ * training (train.py:534-541,702-709).  Two streaming kernels replace what the reference materialises:
+ *
+ * gmpi_mpi_alpha_depth_fwd = LightRenderer.compute_depth (light_renderer.py:82-100): the over-composite of the UN-warped alpha,
+ *   depth[m] = sum_i a_i prod_{j<i}(1 - a_j + 1e-10) plane_d[i]  -> depth [M,1,Ht,Wt].  alpha of plane i of MPI m is read at
+ *   alpha[m * mpi_stride + i * plane_stride + texel] (strides in floats): the expanded stack (alpha = rgba + 3*Ht*Wt, plane_stride
+ *   = 4*Ht*Wt, mpi_stride = N*4*Ht*Wt) or the factored alpha [M,N,1,Ht,Wt] (plane_stride = Ht*Wt).  transmittance [M,N,Ht,Wt] is
+ *   optional (training: saved for the backward).  gmpi_mpi_alpha_depth_bwd: d sum(depth * g_depth) / d alpha into g_alpha with its
+ *   own strides (e.g. channel 3 of a g_rgba stack).
+ * gmpi_mpi_apply_shading_fwd = the last step of LightRenderer.render (light_renderer.py:190-199): out[m,i,c] =
+ *   clip(rgba[m,i,c] * shade[m], 0, 1) for the colour channels, alpha copied: the new [M,N,4,Ht,Wt] MPI in one pass.
+ *   _bwd: gradients w.r.t. rgba and shade [M,1,Ht,Wt] (torch.clip's closed-interval mask).
+ */
+int gmpi_mpi_alpha_depth_fwd(const float* alpha, long long mpi_stride, long long plane_stride, const float* plane_d,
+                             float* depth, float* transmittance, int M, int N, int Ht, int Wt, void* stream);
+int gmpi_mpi_alpha_depth_bwd(const float* alpha, long long mpi_stride, long long plane_stride, const float* plane_d,
+                             const float* transmittance, const float* g_depth, float* g_alpha, long long g_mpi_stride,
+                             long long g_plane_stride, int M, int N, int Ht, int Wt, void* stream);
+int gmpi_mpi_apply_shading_fwd(const float* rgba, const float* shade, float* out, int M, int N, int Ht, int Wt, void* stream);
+int gmpi_mpi_apply_shading_bwd(const float* rgba, const float* shade, const float* g_out, float* g_rgba, float* g_shade,
+                               int M, int N, int Ht, int Wt, void* stream);
+
+/*
  * Range checks of MPIRenderer.render (mpi_renderer.py:447-449) and MPI.check_shapes
  * (mpi.py:185-187) in one streaming pass: sets GMPI_FLAG_RGBA_RANGE / GMPI_FLAG_ALPHA_RANGE.
  */

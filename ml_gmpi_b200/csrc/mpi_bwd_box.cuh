@@ -15,10 +15,10 @@
 // dense, coalesced red.global of the finished sums is bound only by the DRAM read-modify-write of the gradient.  Hence:
 //   * every (tile, plane) has a GRADIENT BOX in shared memory with exactly the layout of the staged plane box
 //     ([row][channel][x], same index as the taps);
-//   * consumers add their 16 contributions per pixel with `red.shared.add.s32` on FIXED-POINT values: c * 2^(21-e) rounded to
-//     nearest (one FFMA against the 1.5*2^23 constant), where 2^e bounds every contribution of the tile (computed from the
-//     tile's upstream gradients, see tile_scale_exponent).  22 bits per contribution relative to that bound, exact (order
-//     independent) integer sums -- the accumulation is more repeatable than fp32 atomics and well inside the 1e-4 bar;
+//   * consumers add their 16 contributions per pixel with `red.shared.add.s32` on FIXED-POINT values: c * 2^(26-e) rounded to
+//     nearest (three FMAs against magic constants, no F2I), where 2^e bounds every contribution of the tile (computed from the
+//     tile's upstream gradients, see tile_scale_exponent).  26 bits per contribution relative to that bound, exact (order
+//     independent) integer sums: more repeatable than fp32 atomics, a few 1e-6 of the largest gradient in error;
 //   * three FLUSHER warps convert a finished box to fp32 and add it to g_rgba with coalesced `red.global.add.v4.f32`
 //     (skipping all-zero quads and texels outside the texture) and re-zero it, while the consumers fill the other box.
 // Out-of-texture taps need no predication: they land in box cells that lie outside the texture, which the flush drops
@@ -57,7 +57,7 @@ struct __align__(16) GradMeta {
     int bx0, by0;        // texel coordinates of box element [0][.][0]
     int rows, cls;       // staged rows (0: nothing in the box), width class (bw = kMinBW + cls * kBWStep)
     int plane;           // m * N + i
-    float scale;         // 2^(e-21): fixed point -> fp32
+    float scale;         // 2^(e - kFixBits): fixed point -> fp32
     int mpi, bg;         // factored MPI: m, and whether this plane's colour gradient goes to g_bg_rgb (last plane)
 };
 constexpr int kBwdAlphaOff = 3 * kMaxBW * kBwdMaxBH;     // factored MPI: alpha box behind the colour box (floats / ints)
@@ -86,16 +86,33 @@ __device__ __noinline__ void scatter_pixel_global(const GradChans gch, int Wt, i
     }
 }
 
-// Fixed-point exponent of a tile: every contribution c of the tile satisfies |c| <= 4 * qmax < 2^e, where
+// Fixed point.  Every contribution c of a tile satisfies |c| <= 2 qmax, where
 // qmax = max over the tile's pixels of |G_r| + |G_g| + |G_b| + |G_d (ray . z_dir)| * max_i |scale_i|:
 //   |dL/d rgb contribution| = |G_c| a T w <= qmax;   |dL/d a contribution| = T |q - R| w <= 2 qmax   (rgb, a, T, w in [0,1];
-//   R is a sub-convex combination of the q's) -- and a factor 2 of slack for inputs that leave [0,1] by rounding.
-// Contributions are rounded to multiples of 2^(e-21), so |c| * 2^(21-e) < 2^21 and a texel may collect 2^9 of them in int32.
+//   R is a sub-convex combination of the q's).  With 2^e > 4 qmax (a factor 2 of slack for inputs that leave [0,1] by rounding)
+// contributions are rounded to multiples of 2^(e - kFixBits): |c| 2^(kFixBits - e) < 2^(kFixBits - 1), i.e. 25 bits + sign per
+// contribution (finer than the fp32 accumulation it replaces whenever the running sum is within 4x of the bound), and a texel
+// may collect 2^(31 - kFixBits + 1) = 64 contributions of maximum size in int32 -- each pixel has one footprint per plane, so
+// that takes a 8x8 minification... of the PIXEL grid onto one texel (scale < 1/4) at maximum gradient everywhere; wrap-around
+// beyond that is the documented limit of this kernel (the direct kernel has none).
+constexpr int kFixBits = 26, kFixSplit = 4;              // low kFixSplit bits come from the second conversion step
+constexpr float kMagicHi = 12582912.0f * 16.0f;          // 1.5 * 2^(23 + kFixSplit): ulp = 2^kFixSplit
+constexpr int kMagicHiBits = 0x4b400000 + (kFixSplit << 23);
 __device__ __forceinline__ int tile_scale_exponent(float qmax) {
     const float b = 4.0f * qmax;
     if (!(b > 0.0f)) return 0;
     int e = (int)((__float_as_uint(b) >> 23) & 0xffu) - 126;     // 2^e > b  (b = 1.m * 2^(E-127) < 2^(E-126))
-    return max(-100, min(100, e));
+    return max(-90, min(90, e));
+}
+// RN(x) for |x| < 2^(22 + kFixSplit), two pixels at once, as integers: the high part is read from the mantissa of x + 1.5 * 2^27
+// (a multiple of 16), the exact remainder (|r| <= 8) from the mantissa of r + 1.5 * 2^23.  x = vF * w is never formed: both steps
+// are FMAs on the exact product.
+__device__ __forceinline__ void fix2(f2 vF, f2 w, int& ia, int& ib) {
+    const f2 t1 = fma2(vF, w, splat(kMagicHi));
+    const f2 nhi = fma2(t1, splat(-1.0f), splat(kMagicHi));      // -(high part), exact
+    const f2 t2 = add2(fma2(vF, w, nhi), splat(kFloorMagic));    // remainder, rounded to an integer
+    ia = ((__float_as_int(t1.x) - kMagicHiBits) << kFixSplit) + (__float_as_int(t2.x) - kFloorMagicBits);
+    ib = ((__float_as_int(t1.y) - kMagicHiBits) << kFixSplit) + (__float_as_int(t2.y) - kFloorMagicBits);
 }
 
 // Fast body: four pixels (two packed pairs) from a staged box of compile-time width BW, contributions into the gradient box.
@@ -157,7 +174,6 @@ template <int BW, int AOFF = 0>
 __device__ __forceinline__ void box_scatter(int* __restrict__ gb, const int (&idx)[kPix], const int (&jdx)[kPix], const f2 (&w4)[kPairs][4],
                                             const f2 (&val)[kPairs][4], f2 Fs) {
     constexpr int RP = AOFF ? 3 * BW : 4 * BW, AP = AOFF ? BW : 4 * BW;
-    const f2 magic = splat(kFloorMagic);
 #pragma unroll
     for (int P = 0; P < kPairs; ++P) {
 #pragma unroll
@@ -168,11 +184,11 @@ __device__ __forceinline__ void box_scatter(int* __restrict__ gb, const int (&id
             const f2 vF = mul2(val[P][ch], Fs);                      // exact (power of two)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                // RN(vF * w) as an integer in the mantissa of t (|vF * w| < 2^21): one packed FFMA for two pixels
-                const f2 t = fma2(vF, w4[P][k], magic);
+                int ca, cb;
+                fix2(vF, w4[P][k], ca, cb);
                 const int off = (k & 1) + (k >> 1) * pitch;
-                atomicAdd(ga + off, __float_as_int(t.x) - kFloorMagicBits);
-                atomicAdd(gq + off, __float_as_int(t.y) - kFloorMagicBits);
+                atomicAdd(ga + off, ca);
+                atomicAdd(gq + off, cb);
             }
         }
     }
@@ -193,23 +209,31 @@ __device__ __forceinline__ void flush_box(int* __restrict__ gb, const GradMeta& 
         dst[0] = b; dst[1] = b + tex; dst[2] = b + 2 * tex; dst[3] = b + 3 * tex;
     }
     const float sc = gm.scale;
-    for (int r = fw; r < gm.rows; r += kBwdFlushWarps) {
-        const int ty = gm.by0 + r;                                   // warp-uniform
-        const bool row_ok = (unsigned)ty < (unsigned)Ht;
-        // BW quads per box row: channel ch, quad x4.  Expanded: [row][4][BW]; factored: [row][3][BW] + alpha box [row][BW].
-        int4* crow = reinterpret_cast<int4*>(gb + r * (FAC ? 3 * BW : 4 * BW));
-        int4* arow = reinterpret_cast<int4*>(gb + (FAC ? kBwdAlphaOff + r * BW : r * 4 * BW + 3 * BW));
-        for (int j = lane; j < BW; j += 32) {
-            const int ch = j / Q, x4 = j - ch * Q;
-            int4* cell = ch < 3 ? crow + j : arow + x4;
-            const int4 a = *cell;
-            if ((a.x | a.y | a.z | a.w) == 0) continue;              // untouched halo: nothing to add, nothing to clear
-            *cell = make_int4(0, 0, 0, 0);
-            const int tx = gm.bx0 + 4 * x4;
-            if (row_ok && (unsigned)tx < (unsigned)Wt) {             // bx0 % 4 == 0 and Wt % 4 == 0: a quad is inside or outside as a whole
-                float* d = ch == 0 ? dst[0] : ch == 1 ? dst[1] : ch == 2 ? dst[2] : dst[3];
-                red_add_v4(d + (size_t)ty * Wt + tx, (float)a.x * sc, (float)a.y * sc, (float)a.z * sc, (float)a.w * sc);
-            }
+    constexpr int kRowsPerWarp = (kBwdMaxBH + kBwdFlushWarps - 1) / kBwdFlushWarps;
+    // BW quads per box row: channel ch, quad x4.  Expanded: [row][4][BW]; factored: [row][3][BW] + alpha box [row][BW].
+    // All rows of this warp are loaded before any is processed: the flush is a latency chain otherwise (LDS -> test -> RED).
+    for (int j = lane; j < BW; j += 32) {
+        const int ch = j / Q, x4 = j - ch * Q;
+        const int cell0 = FAC ? (ch < 3 ? j * 4 : kBwdAlphaOff + x4 * 4) : j * 4;          // int offset inside a row
+        constexpr int kColPitch = FAC ? 3 * BW : 4 * BW;
+        const int pitch = (FAC && ch == 3) ? BW : kColPitch;
+        int4 a[kRowsPerWarp];
+#pragma unroll
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+            const int r = fw + k * kBwdFlushWarps;
+            a[k] = r < gm.rows ? *reinterpret_cast<const int4*>(gb + r * pitch + cell0) : make_int4(0, 0, 0, 0);
+        }
+        const int tx = gm.bx0 + 4 * x4;
+        const bool col_ok = (unsigned)tx < (unsigned)Wt;          // bx0 % 4 == 0 and Wt % 4 == 0: a quad is inside or outside as a whole
+        float* d = (ch == 0 ? dst[0] : ch == 1 ? dst[1] : ch == 2 ? dst[2] : dst[3]) + tx;
+#pragma unroll
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+            const int r = fw + k * kBwdFlushWarps;
+            if ((a[k].x | a[k].y | a[k].z | a[k].w) == 0) continue;  // untouched halo (or a row beyond the box): nothing to add or clear
+            *reinterpret_cast<int4*>(gb + r * pitch + cell0) = make_int4(0, 0, 0, 0);
+            const int ty = gm.by0 + r;
+            if (col_ok && (unsigned)ty < (unsigned)Ht)
+                red_add_v4(d + (size_t)ty * Wt, (float)a[k].x * sc, (float)a[k].y * sc, (float)a[k].z * sc, (float)a[k].w * sc);
         }
     }
 }
@@ -347,8 +371,8 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                 qmax = __uint_as_float(s_qmax[slot]);
             }
             const int e_fix = tile_scale_exponent(qmax);
-            const f2 Fs = splat(__uint_as_float((unsigned)(127 + 21 - e_fix) << 23));      // 2^(21-e)
-            const float inv_scale = __uint_as_float((unsigned)(127 - 21 + e_fix) << 23);    // 2^(e-21)
+            const f2 Fs = splat(__uint_as_float((unsigned)(127 + kFixBits - e_fix) << 23));      // 2^(kFixBits - e)
+            const float inv_scale = __uint_as_float((unsigned)(127 - kFixBits + e_fix) << 23);    // 2^(e - kFixBits)
 
             const bool idle = py0 + kPairs * warp >= p.H;      // warp-uniform: no row of this warp is inside the image
 #pragma unroll

@@ -15,6 +15,7 @@
 #include "mpi_common.cuh"
 #include "mpi_fwd_staged.cuh"
 #include "mpi_bwd_box.cuh"
+#include "mpi_light.cuh"
 
 namespace gmpi {
 
@@ -747,6 +748,74 @@ int gmpi_debug_cam_rays(const float* cam, float* ray_dir, int V, int H, int W, v
     if (!cam || !ray_dir || V < 1 || H < 1 || W < 1) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad argument");
     dim3 grid((unsigned)(((size_t)H * W + 255) / 256), V);
     mpi_debug_cam_rays_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cam, ray_dir, V, H, W);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LightRenderer kernels (gmpi/core/light_renderer.py), SURVEY.md 8(f) N3
+// ------------------------------------------------------------------------------------------
+static int check_alpha_view(const float* alpha, long long mpi_stride, long long plane_stride, int M, int N, int Ht, int Wt) {
+    if (!alpha) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (M < 1 || N < 1 || Ht < 1 || Wt < 1 || M > 65535) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (((size_t)Ht * Wt) % 4 != 0 || plane_stride % 4 != 0 || mpi_stride % 4 != 0 || ((uintptr_t)alpha & 15) != 0)
+        return fail(GMPI_ERR_UNSUPPORTED, "alpha planes must be 16-byte aligned with Ht*Wt %% 4 == 0 (float4 streaming)");
+    return GMPI_OK;
+}
+
+int gmpi_mpi_alpha_depth_fwd(const float* alpha, long long mpi_stride, long long plane_stride, const float* plane_d, float* depth,
+                             float* transmittance, int M, int N, int Ht, int Wt, void* stream) {
+    int rc = check_alpha_view(alpha, mpi_stride, plane_stride, M, N, Ht, Wt);
+    if (rc) return rc;
+    if (!plane_d || !depth) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    const long long tex4 = (long long)Ht * Wt / 4;
+    AlphaView a{alpha, mpi_stride, plane_stride};
+    dim3 grid((unsigned)((tex4 + 255) / 256), M);
+    if (transmittance) mpi_alpha_depth_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a, plane_d, depth, transmittance, N, tex4);
+    else mpi_alpha_depth_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a, plane_d, depth, nullptr, N, tex4);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_alpha_depth_bwd(const float* alpha, long long mpi_stride, long long plane_stride, const float* plane_d,
+                             const float* transmittance, const float* g_depth, float* g_alpha, long long g_mpi_stride,
+                             long long g_plane_stride, int M, int N, int Ht, int Wt, void* stream) {
+    int rc = check_alpha_view(alpha, mpi_stride, plane_stride, M, N, Ht, Wt);
+    if (rc) return rc;
+    if (!plane_d || !transmittance || !g_depth || !g_alpha) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (g_plane_stride % 4 != 0 || g_mpi_stride % 4 != 0 || ((uintptr_t)g_alpha & 15) != 0)
+        return fail(GMPI_ERR_UNSUPPORTED, "g_alpha planes must be 16-byte aligned");
+    const long long tex4 = (long long)Ht * Wt / 4;
+    AlphaView a{alpha, mpi_stride, plane_stride};
+    dim3 grid((unsigned)((tex4 + 255) / 256), M);
+    mpi_alpha_depth_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, plane_d, transmittance, g_depth, g_alpha, g_mpi_stride,
+                                                                        g_plane_stride, N, tex4);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_apply_shading_fwd(const float* rgba, const float* shade, float* out, int M, int N, int Ht, int Wt, void* stream) {
+    if (!rgba || !shade || !out) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (M < 1 || N < 1 || Ht < 1 || Wt < 1 || M > 65535 || N > 65535) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (((size_t)Ht * Wt) % 4 != 0 || (((uintptr_t)rgba | (uintptr_t)shade | (uintptr_t)out) & 15) != 0)
+        return fail(GMPI_ERR_UNSUPPORTED, "tensors must be 16-byte aligned with Ht*Wt %% 4 == 0 (float4 streaming)");
+    const long long tex4 = (long long)Ht * Wt / 4;
+    dim3 grid((unsigned)((tex4 + 255) / 256), N, M);
+    mpi_apply_shading_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rgba, shade, out, N, tex4);
+    GMPI_CUDA_OK(cudaGetLastError());
+    return GMPI_OK;
+}
+
+int gmpi_mpi_apply_shading_bwd(const float* rgba, const float* shade, const float* g_out, float* g_rgba, float* g_shade, int M, int N,
+                               int Ht, int Wt, void* stream) {
+    if (!rgba || !shade || !g_out || !g_rgba || !g_shade) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    if (M < 1 || N < 1 || Ht < 1 || Wt < 1 || M > 65535) return fail(GMPI_ERR_INVALID_ARGUMENT, "bad sizes");
+    if (((size_t)Ht * Wt) % 4 != 0 ||
+        (((uintptr_t)rgba | (uintptr_t)shade | (uintptr_t)g_out | (uintptr_t)g_rgba | (uintptr_t)g_shade) & 15) != 0)
+        return fail(GMPI_ERR_UNSUPPORTED, "tensors must be 16-byte aligned with Ht*Wt %% 4 == 0 (float4 streaming)");
+    const long long tex4 = (long long)Ht * Wt / 4;
+    dim3 grid((unsigned)((tex4 + 255) / 256), M);
+    mpi_apply_shading_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rgba, shade, g_out, g_rgba, g_shade, N, tex4);
     GMPI_CUDA_OK(cudaGetLastError());
     return GMPI_OK;
 }
