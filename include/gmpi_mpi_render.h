@@ -152,7 +152,8 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
  *                                                identical to rendering the expanded stack.
  *   camera, one of
  *     ray_dir [V,3,H,W] + eye [V,3] + z_dir [V,3]   the reference's tensors (parity mode: bit-exact texel coordinates)
- *     cam [V,16] = {focal, cx, cy, pixel-centre offset (0.5), R row-major (9), eye (3)}
+ *     cam [V,16] = {f0, f1, f2 (the fp64 focal length as three fp32 pieces with f0 + f1 + f2 == focal exactly), pixel-centre
+ *                   offset (0.5), R row-major (9), eye (3)}; the principal point is (W/2, H/2) (cam_utils.py:20)
  *                                                fast mode: rays generated in the kernel with camera.py:53-118,182-211's
  *                                                arithmetic (fp64 camera ray -> fp32 -> fp32 rotation); saves the [V,3,H,W]
  *                                                tensor and its upload.  Forward only.
@@ -202,6 +203,10 @@ typedef struct gmpi_render_desc {
     uint32_t* flags;
     void* stream;
 } gmpi_render_desc;
+
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: lets a caller zero the gradient buffers on a SIDE stream while the training forward
+ * runs (the memset is a copy-engine operation, the forward kernel owns every SM), instead of GMPI_ZERO_GRAD's in-line memset. */
+int gmpi_mpi_zero_async(void* ptr, size_t bytes, void* stream);
 
 int gmpi_mpi_render_fwd_ex(const gmpi_render_desc* desc);
 int gmpi_mpi_render_bwd_ex(const gmpi_render_desc* desc);

@@ -28,7 +28,7 @@ EXPORTS = [
     "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_plane_coords_packed", "gmpi_debug_tile_walk",
     "gmpi_mpi_render_fwd_plan", "gmpi_mpi_render_fwd_ex", "gmpi_mpi_render_bwd_ex", "gmpi_mpi_render_host_ex",
     "gmpi_debug_tile_walk_ex", "gmpi_debug_cam_rays",
-    "gmpi_mpi_alpha_depth_fwd", "gmpi_mpi_alpha_depth_bwd", "gmpi_mpi_apply_shading_fwd", "gmpi_mpi_apply_shading_bwd",
+    "gmpi_mpi_zero_async", "gmpi_mpi_alpha_depth_fwd", "gmpi_mpi_alpha_depth_bwd", "gmpi_mpi_apply_shading_fwd", "gmpi_mpi_apply_shading_bwd",
 ]
 
 OPT_U8_ROUND_HALF_UP = 16
@@ -118,6 +118,8 @@ def load():
     for fn in (lib.gmpi_mpi_render_fwd_ex, lib.gmpi_mpi_render_bwd_ex):
         fn.restype = i
         fn.argtypes = [ctypes.POINTER(RenderDesc)]
+    lib.gmpi_mpi_zero_async.restype = i
+    lib.gmpi_mpi_zero_async.argtypes = [vp, ctypes.c_size_t, vp]
     ll = ctypes.c_longlong
     lib.gmpi_mpi_alpha_depth_fwd.restype = i
     lib.gmpi_mpi_alpha_depth_fwd.argtypes = [vp, ll, ll, vp, vp, vp, i, i, i, i, vp]

@@ -59,10 +59,17 @@ class PinholeCamera:
 
 
 def cam_params(c2w: torch.Tensor, focal: float, height: int, width: int, ray_from_pix_center: bool = True) -> torch.Tensor:
-    """[V,16] fp32 = {focal, cx, cy, pixel-centre offset, R row-major (9), eye (3)} per view: the `cam` input of the kernels' fast
-    mode (rays generated in the kernel with PinholeCamera's arithmetic instead of uploading ray_dir [V,3,H,W])."""
+    """[V,16] fp32 = {f0, f1, f2, pixel-centre offset, R row-major (9), eye (3)} per view: the `cam` input of the kernels' fast
+    mode (rays generated in the kernel with PinholeCamera's arithmetic instead of uploading ray_dir [V,3,H,W]).  The focal
+    length is an fp64 number (focal_from_fov); f0 + f1 + f2 is its exact three-piece fp32 expansion, so the kernel's fp64 camera
+    ray is bit-identical to `_cam_dirs64`.  The principal point is (width/2, height/2), which the kernel derives itself."""
     V = c2w.shape[0]
-    head = torch.tensor([float(focal), width / 2.0, height / 2.0, 0.5 if ray_from_pix_center else 0.0], dtype=torch.float32,
+    f = np.float64(focal)
+    f0 = np.float32(f)
+    f1 = np.float32(f - np.float64(f0))
+    f2 = np.float32(f - np.float64(f0) - np.float64(f1))
+    assert np.float64(f0) + np.float64(f1) + np.float64(f2) == f
+    head = torch.tensor([float(f0), float(f1), float(f2), 0.5 if ray_from_pix_center else 0.0], dtype=torch.float32,
                         device=c2w.device).expand(V, 4)
     return torch.cat([head, c2w[:, :3, :3].reshape(V, 9).float(), c2w[:, :3, 3].float()], dim=1).contiguous()
 

@@ -290,7 +290,7 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                 const int b = f_box;
                 const uint32_t ph = f_phase;
                 if (++f_box == kBwdBoxes) { f_box = 0; f_phase ^= 1u; }
-                mbar_wait(&g_full[b], ph);
+                mbar_wait_sleep(&g_full[b], ph);
                 const GradMeta gm = s_gmeta[b];
                 int* gb = s_grad + b * kBwdPlaneFloats;
                 if (gm.rows > 0) {

@@ -33,7 +33,7 @@ struct RenderParams {
     // training: transmittance before each plane, [V,N,H,W]; written by the forward, read by the staged backward (nullable)
     float* transmittance;
     // fast mode (opt-in): rays generated in the kernel from the pinhole camera of each view instead of read from ray_dir
-    // (camera.py:182-211).  cam [V,16] = {focal, cx, cy, pixel-centre offset, R row-major (9), eye (3)}; ray_dir may be NULL
+    // (camera.py:182-211).  cam [V,16] = {focal as three fp32 pieces (exact fp64 sum), pixel-centre offset, R row-major (9), eye (3)}
     const float* cam;
     // video epilogue (opt-in, render_video.py:118-126): uint8 HWC colour [V,H,W,3] and depth [V,H,W,1] instead of color/depth
     uint8_t* video_rgb;
@@ -83,8 +83,10 @@ constexpr uint32_t kOptVec4Stores = 1u << 16;   // W % 4 == 0 and all output bas
 
 // Pinhole ray of pixel (px, py) of a view, the arithmetic of ml_gmpi_b200.camera.PinholeCamera (camera.py:53-76,98-118,182-211
 // of the reference): camera-space direction in fp64, normalised, rounded to fp32, rotated to world space in fp32.
-__device__ __forceinline__ void cam_ray(const float* __restrict__ cam, int px, int py, float& rx, float& ry, float& rz) {
-    const double focal = (double)__ldg(cam), cx = (double)__ldg(cam + 1), cy = (double)__ldg(cam + 2), off = (double)__ldg(cam + 3);
+__device__ __forceinline__ void cam_ray(const float* __restrict__ cam, int px, int py, int H, int W, float& rx, float& ry, float& rz) {
+    // the focal length is an fp64 quantity on the host (w / (2 tan(fov/2))): it travels as three fp32 pieces whose exact sum it is
+    const double focal = __dadd_rn(__dadd_rn((double)__ldg(cam), (double)__ldg(cam + 1)), (double)__ldg(cam + 2));
+    const double off = (double)__ldg(cam + 3), cx = 0.5 * (double)W, cy = 0.5 * (double)H;     // principal point (w/2, h/2), cam_utils.py:20
     const double xs = __ddiv_rn(__dsub_rn(__dadd_rn((double)px, off), cx), focal);      // K^-1 [u v 1], camera.py:63-66
     const double ys = __ddiv_rn(__dsub_rn(__dadd_rn((double)py, off), cy), focal);
     const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(xs, xs), __dmul_rn(ys, ys)), 1.0));   // camera.py:98-105
@@ -98,7 +100,7 @@ __device__ __forceinline__ void cam_ray(const float* __restrict__ cam, int px, i
 // Ray of pixel (px, py) of view v: read from ray_dir (the reference's tensor: parity mode) or generated (fast mode).
 __device__ __forceinline__ void load_ray(const RenderParams& p, int v, int px, int py, size_t img, float& rx, float& ry, float& rz) {
     if (p.cam) {
-        cam_ray(p.cam + 16 * (size_t)v, px, py, rx, ry, rz);
+        cam_ray(p.cam + 16 * (size_t)v, px, py, p.H, p.W, rx, ry, rz);
     } else {
         const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)py * p.W + px;
         rx = __ldg(rd); ry = __ldg(rd + img); rz = __ldg(rd + 2 * img);

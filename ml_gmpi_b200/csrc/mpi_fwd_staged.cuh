@@ -348,7 +348,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             const int bw = kMinBW + k * kBWStep;
             const int n_ops = mode == 0 ? (need_h + kRowsPerOp - 1) / kRowsPerOp : 0;
             const int rows = n_ops * kRowsPerOp;
-            mbar_wait(&s_empty[s], ph ^ 1);
+            mbar_wait_sleep(&s_empty[s], ph ^ 1);
             if (lane == 0) {
                 StageMeta mt;
                 mt.cx = kFloorMagicBits + bx0; mt.cy = kFloorMagicBits + by0;

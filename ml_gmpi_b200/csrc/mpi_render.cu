@@ -316,7 +316,7 @@ __global__ void mpi_debug_cam_rays_kernel(const float* __restrict__ cam, float* 
     const int v = blockIdx.y;
     if (pix >= img) return;
     float rx, ry, rz;
-    cam_ray(cam + 16 * (size_t)v, (int)(pix % W), (int)(pix / W), rx, ry, rz);
+    cam_ray(cam + 16 * (size_t)v, (int)(pix % W), (int)(pix / W), H, W, rx, ry, rz);
     float* o = ray_dir + (size_t)v * 3 * img + pix;
     o[0] = rx; o[img] = ry; o[2 * img] = rz;
 }
@@ -675,6 +675,12 @@ int gmpi_mpi_render_bwd_saved(const float* rgba, const int32_t* view2mpi, const 
     RenderParams p = params_classic(rgba, view2mpi, dhw, ray_dir, eye, z_dir, M, V, N, Ht, Wt, H, W, options);
     p.g_color = g_color; p.g_depth = g_depth; p.g_rgba = g_rgba; p.transmittance = const_cast<float*>(transmittance);
     return launch_bwd(p, (cudaStream_t)stream);
+}
+
+int gmpi_mpi_zero_async(void* ptr, size_t bytes, void* stream) {
+    if (!ptr && bytes) return fail(GMPI_ERR_INVALID_ARGUMENT, "null pointer");
+    GMPI_CUDA_OK(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+    return GMPI_OK;
 }
 
 int gmpi_mpi_render_fwd_ex(const gmpi_render_desc* d) {

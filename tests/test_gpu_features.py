@@ -193,3 +193,36 @@ def test_host_entry_point_with_factored_cam_and_video_forms():
     assert flags[0] == 0
     assert torch.equal(o_rgb, u8.cpu()) and torch.equal(o_dep, d8.cpu())
     _lib.check(lib.gmpi_mpi_release_host_cache())
+
+
+def test_video_service_equals_the_per_view_reference_loop():
+    """service.render_video_frames (one launch, uint8 epilogue, one D2H) == generate_img's loop (render_video.py:95-126): one
+    MPIRenderer.render per angle, then the numpy conversion lines."""
+    from ml_gmpi_b200 import service
+    from ml_gmpi_b200.renderer import MPIRenderer
+    d = dev()
+    N, T, I = 32, 256, 256
+    r = MPIRenderer(n_mpi_planes=N, plane_min_d=FFHQ["plane_min_d"], plane_max_d=FFHQ["plane_max_d"],
+                    plan_spatial_enlarge_factor=FFHQ["enlarge_factor"], plane_distances_sample_method="inverse", cam_fov=12.6,
+                    sphere_center_z=1.0, sphere_r=1.0, horizontal_mean=0.0, horizontal_std=0.289, vertical_mean=0.0,
+                    vertical_std=0.127, cam_pose_n_truncated_stds=2, cam_sample_method="truncated_gaussian",
+                    mpi_align_corners=True, use_confined_volume=True, device=d)
+    gen = torch.Generator(device=d).manual_seed(3)
+    mpi = torch.rand((1, N, 4, T, T), generator=gen, device=d)
+    mpi[:, -1, 3] = 1.0
+    angles = service.sweep_angles(6, True)
+    near, far = 0.95, 1.12                                                 # curriculums.py:110-111 ray_start / ray_end
+    dhw = r.static_mpi_plane_dhws.to(d).reshape(1, N, 3)
+    img, depth = service.render_video_frames(mpi, dhw, angles, img_size=I, fov_deg=12.6, ray_start=near, ray_end=far,
+                                             sphere_center=r.sphere_center, sphere_r=r.sphere_r)
+    assert img.shape == (6, I, I, 3) and depth.shape == (6, I, I, 1)
+    for i, a in enumerate(angles):
+        im, dm, _, _ = r.render(mpi, I, I, horizontal_mean=a, horizontal_std=0.0, vertical_mean=0.0, vertical_std=0.0,
+                                assert_not_out_of_last_plane=True)
+        ref_img, ref_depth = _video_reference(im, dm, near, far)
+        assert np.array_equal(img[i].numpy(), ref_img[0]) and np.array_equal(depth[i].numpy(), ref_depth[0]), i
+    # the fast mode (rays generated in the kernel) differs from the parity frames by at most one grey level on a few pixels
+    fast, _ = service.render_video_frames(mpi, dhw, angles, img_size=I, fov_deg=12.6, ray_start=near, ray_end=far,
+                                          sphere_center=r.sphere_center, sphere_r=r.sphere_r, fast_rays=True)
+    diff = (fast.to(torch.int16) - img.to(torch.int16)).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.02
