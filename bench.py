@@ -529,8 +529,10 @@ def make_gather_or_fallback(job, frames_per_rank, H, W):
     if job.world == 1:
         return None, "none"
     try:    # all-gather fused into the render epilogue: peer stores into symmetric memory over NVLink
-        return (be.make_gather(frames_per_rank, H, W),
-                "fused: render epilogue stores frames into every rank's symmetric-memory buffer (NVLink), 1 device barrier per step")
+        gather = be.make_gather(frames_per_rank, H, W)
+        how = ("one float4 store per quad to the NVLS multicast address, the switch replicates" if getattr(gather, "multicast", False)
+               else "float4 peer stores into every rank's symmetric-memory buffer")
+        return gather, f"fused: render epilogue, {how} (NVLink), double-buffered, 1 device barrier per step"
     except Exception as ex:
         if job.rank == 0:
             print(f"[bench] symmetric memory unavailable ({type(ex).__name__}: {ex}); using ncclAllGather", file=sys.stderr)

@@ -46,6 +46,10 @@ struct BwdRing {
     static constexpr int kTileRows = kBwdTileH, kRingStages = kBwdStages, kBoxMaxH = kBwdMaxBH;
     static constexpr int kPlaneFloats = kBwdPlaneFloats, kStride = kBwdStride;
     static constexpr bool kReverse = true;       // planes back to front; each stage also carries the tile's saved transmittance
+#ifndef GMPI_BWD_SLEEP
+#define GMPI_BWD_SLEEP 1
+#endif
+    static constexpr bool kSleepPolls = GMPI_BWD_SLEEP != 0;
 };
 
 struct GradPairs {
@@ -57,8 +61,9 @@ struct __align__(16) GradMeta {
     int bx0, by0;        // texel coordinates of box element [0][.][0]
     int rows, cls;       // staged rows (0: nothing in the box), width class (bw = kMinBW + cls * kBWStep)
     int plane;           // m * N + i
-    float scale;         // 2^(e - kFixBits): fixed point -> fp32
-    int mpi, bg;         // factored MPI: m, and whether this plane's colour gradient goes to g_bg_rgb (last plane)
+    float scale;         // alpha channel: 2^(e_a - kFixBits), fixed point -> fp32
+    int mpi_bg;          // factored MPI: 2 * m + (1 if this plane's colour gradient goes to g_bg_rgb: the last plane)
+    float scale_rgb;     // colour channels: 2^(e_rgb - kFixBitsRgb)
 };
 constexpr int kBwdAlphaOff = 3 * kMaxBW * kBwdMaxBH;     // factored MPI: alpha box behind the colour box (floats / ints)
 
@@ -95,7 +100,11 @@ __device__ __noinline__ void scatter_pixel_global(const GradChans gch, int Wt, i
 // may collect 2^(31 - kFixBits + 1) = 64 contributions of maximum size in int32 -- each pixel has one footprint per plane, so
 // that takes a 8x8 minification... of the PIXEL grid onto one texel (scale < 1/4) at maximum gradient everywhere; wrap-around
 // beyond that is the documented limit of this kernel (the direct kernel has none).
-constexpr int kFixBits = 26, kFixSplit = 4;              // low kFixSplit bits come from the second conversion step
+constexpr int kFixBits = 26, kFixSplit = 4;              // alpha: low kFixSplit bits come from the second conversion step
+// The three colour channels have their own, tighter bound -- |dL/d rgb contribution| = |G_c| a T w <= gmax = max |G_c| over the
+// tile, without the depth term and the factor 2 of the alpha bound -- and take the one-step conversion: 2^e_rgb > 2 gmax,
+// contributions rounded to multiples of 2^(e_rgb - 21) (|c| 2^(21 - e_rgb) < 2^20, far inside the 2^22 the magic constant allows).
+constexpr int kFixBitsRgb = 21;
 constexpr float kMagicHi = 12582912.0f * 16.0f;          // 1.5 * 2^(23 + kFixSplit): ulp = 2^kFixSplit
 constexpr int kMagicHiBits = 0x4b400000 + (kFixSplit << 23);
 __device__ __forceinline__ int tile_scale_exponent(float qmax) {
@@ -117,15 +126,38 @@ __device__ __forceinline__ void fix2(f2 vF, f2 w, int& ia, int& ib) {
 
 // Fast body: four pixels (two packed pairs) from a staged box of compile-time width BW, contributions into the gradient box.
 // Returns false (nothing sampled, R unchanged) if any footprint is not inside the box.
+// One (pair, channel) of the scatter: the four bilinear contributions of two pixels into the gradient box.
+template <int PITCH, bool kTwoStep>
+__device__ __forceinline__ void scatter_channel(int* __restrict__ ga, int* __restrict__ gq, f2 vF, const f2 (&w)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int ca, cb;
+        if (!kTwoStep) {     // RN(vF * w) read from the mantissa of one packed FMA
+            const f2 t = fma2(vF, w[k], splat(kFloorMagic));
+            ca = __float_as_int(t.x) - kFloorMagicBits; cb = __float_as_int(t.y) - kFloorMagicBits;
+        } else {
+            fix2(vF, w[k], ca, cb);
+        }
+        const int off = (k & 1) + (k >> 1) * PITCH;
+        atomicAdd(ga + off, ca);
+        atomicAdd(gq + off, cb);
+    }
+}
+
+// Fast body: four pixels (two packed pairs) from a staged box of compile-time width BW: sample, form the gradients, add the 64
+// fixed-point contributions to the gradient box `gb` (same layout as the staged box).  Returns false (nothing sampled, R
+// unchanged, nothing added) if any footprint is not inside the box.
 // AOFF as in sample_pairs: 0 = expanded stage, > 0 = factored (colour box [row][3][BW], alpha box [row][BW] at AOFF).
+// Each pair is scattered as soon as it is formed: keeping both pairs' weights and values alive until a later scatter phase costs
+// ~36 registers and spills.
 template <int BW, int AOFF = 0>
-__device__ __forceinline__ bool bwd_box_pairs(const float* __restrict__ sb, int cx, int cy, int rows2, const CoordPairs& c,
-                                              const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], int (&idx)[kPix], int (&jdx)[kPix],
-                                              f2 (&w4)[kPairs][4], f2 (&val)[kPairs][4]) {
+__device__ __forceinline__ bool bwd_box_pairs(const float* __restrict__ sb, int* __restrict__ gb, int cx, int cy, int rows2, const CoordPairs& c,
+                                              const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], f2 Fs, f2 Fs_rgb) {
     constexpr int RP = AOFF ? 3 * BW : 4 * BW, AP = AOFF ? BW : 4 * BW, A0 = AOFF ? AOFF : 3 * BW;
     const f2 m1 = splat(-1.0f), one = splat(1.0f);
     const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
     f2 fx0[kPairs], fy0[kPairs];
+    int idx[kPix], jdx[kPix];
     bool inbox = true;
 #pragma unroll
     for (int P = 0; P < kPairs; ++P) {
@@ -145,53 +177,34 @@ __device__ __forceinline__ bool bwd_box_pairs(const float* __restrict__ sb, int 
     for (int P = 0; P < kPairs; ++P) {
         const f2 wx1 = fma2(fx0[P], m1, c.ix[P]), wy1 = fma2(fy0[P], m1, c.iy[P]);
         const f2 wy0 = fma2(wy1, m1, one);
-        const f2 w11 = mul2(wx1, wy1), w10 = fma2(w11, m1, wy1), w01 = fma2(w11, m1, wx1), w00 = fma2(w01, m1, wy0);
+        f2 w[4];
+        w[3] = mul2(wx1, wy1); w[2] = fma2(w[3], m1, wy1); w[1] = fma2(w[3], m1, wx1); w[0] = fma2(w[1], m1, wy0);
         const float* ta = sb + idx[2 * P];
         const float* tb = sb + idx[2 * P + 1];
 #define GMPI_TAP(ch)                                                                                           \
-    fma2(make_float2(ta[RP + ch * BW + 1], tb[RP + ch * BW + 1]), w11,                                         \
-         fma2(make_float2(ta[RP + ch * BW], tb[RP + ch * BW]), w10,                                            \
-              fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w01, mul2(make_float2(ta[ch * BW], tb[ch * BW]), w00))))
+    fma2(make_float2(ta[RP + ch * BW + 1], tb[RP + ch * BW + 1]), w[3],                                        \
+         fma2(make_float2(ta[RP + ch * BW], tb[RP + ch * BW]), w[2],                                           \
+              fma2(make_float2(ta[ch * BW + 1], tb[ch * BW + 1]), w[1], mul2(make_float2(ta[ch * BW], tb[ch * BW]), w[0]))))
         const f2 r = GMPI_TAP(0), g = GMPI_TAP(1), b = GMPI_TAP(2);
 #undef GMPI_TAP
         const float* aa = AOFF ? sb + jdx[2 * P] : ta + A0;
         const float* ab = AOFF ? sb + jdx[2 * P + 1] : tb + A0;
-        const f2 a = fma2(make_float2(aa[AP + 1], ab[AP + 1]), w11,
-                          fma2(make_float2(aa[AP], ab[AP]), w10, fma2(make_float2(aa[1], ab[1]), w01, mul2(make_float2(aa[0], ab[0]), w00))));
+        const f2 a = fma2(make_float2(aa[AP + 1], ab[AP + 1]), w[3],
+                          fma2(make_float2(aa[AP], ab[AP]), w[2], fma2(make_float2(aa[1], ab[1]), w[1], mul2(make_float2(aa[0], ab[0]), w[0]))));
         const f2 q = fma2(G.g0[P], r, fma2(G.g1[P], g, fma2(G.g2[P], b, mul2(G.gs[P], c.sc[P]))));
         const f2 d = fma2(R[P], m1, q);                 // q - R
-        const f2 w = mul2(a, T[P]);
+        const f2 wT = mul2(a, T[P]);
         R[P] = fma2(a, d, R[P]);
-        val[P][0] = mul2(G.g0[P], w); val[P][1] = mul2(G.g1[P], w); val[P][2] = mul2(G.g2[P], w);
-        val[P][3] = mul2(T[P], d);                      // dL/d alpha
-        w4[P][0] = w00; w4[P][1] = w01; w4[P][2] = w10; w4[P][3] = w11;
+        // ---- scatter (grid_sampler_2d_backward), fixed point: colour channels one-step, alpha two-step ----
+        const f2 wF = mul2(wT, Fs_rgb);                 // exact (power of two)
+        int* ga = gb + idx[2 * P];
+        int* gq = gb + idx[2 * P + 1];
+        scatter_channel<RP, false>(ga, gq, mul2(G.g0[P], wF), w);
+        scatter_channel<RP, false>(ga + BW, gq + BW, mul2(G.g1[P], wF), w);
+        scatter_channel<RP, false>(ga + 2 * BW, gq + 2 * BW, mul2(G.g2[P], wF), w);
+        scatter_channel<AP, true>(AOFF ? gb + jdx[2 * P] : ga + A0, AOFF ? gb + jdx[2 * P + 1] : gq + A0, mul2(mul2(T[P], d), Fs), w);   // dL/d alpha
     }
     return true;
-}
-
-// The 64 fixed-point adds of a thread's four pixels into the gradient box (`gb` has the staged box's layout).
-template <int BW, int AOFF = 0>
-__device__ __forceinline__ void box_scatter(int* __restrict__ gb, const int (&idx)[kPix], const int (&jdx)[kPix], const f2 (&w4)[kPairs][4],
-                                            const f2 (&val)[kPairs][4], f2 Fs) {
-    constexpr int RP = AOFF ? 3 * BW : 4 * BW, AP = AOFF ? BW : 4 * BW;
-#pragma unroll
-    for (int P = 0; P < kPairs; ++P) {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            int* ga = gb + ((AOFF && ch == 3) ? jdx[2 * P] : idx[2 * P] + ch * BW);
-            int* gq = gb + ((AOFF && ch == 3) ? jdx[2 * P + 1] : idx[2 * P + 1] + ch * BW);
-            const int pitch = ch < 3 ? RP : AP;
-            const f2 vF = mul2(val[P][ch], Fs);                      // exact (power of two)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int ca, cb;
-                fix2(vF, w4[P][k], ca, cb);
-                const int off = (k & 1) + (k >> 1) * pitch;
-                atomicAdd(ga + off, ca);
-                atomicAdd(gq + off, cb);
-            }
-        }
-    }
 }
 
 // Flusher: rows fw, fw + 3, ... of a finished gradient box -> fp32 -> red.global.add.v4.f32, then zero.
@@ -202,13 +215,12 @@ __device__ __forceinline__ void flush_box(int* __restrict__ gb, const GradMeta& 
     // destination slabs of the four channels
     float* dst[4];
     if (FAC) {
-        float* rgb = (gm.bg ? p.g_bg_rgb : p.g_rgb) + (size_t)gm.mpi * 3 * tex;
+        float* rgb = ((gm.mpi_bg & 1) ? p.g_bg_rgb : p.g_rgb) + (size_t)(gm.mpi_bg >> 1) * 3 * tex;
         dst[0] = rgb; dst[1] = rgb + tex; dst[2] = rgb + 2 * tex; dst[3] = p.g_alpha + (size_t)gm.plane * tex;
     } else {
         float* b = p.g_rgba + (size_t)gm.plane * 4 * tex;
         dst[0] = b; dst[1] = b + tex; dst[2] = b + 2 * tex; dst[3] = b + 3 * tex;
     }
-    const float sc = gm.scale;
     constexpr int kRowsPerWarp = (kBwdMaxBH + kBwdFlushWarps - 1) / kBwdFlushWarps;
     // BW quads per box row: channel ch, quad x4.  Expanded: [row][4][BW]; factored: [row][3][BW] + alpha box [row][BW].
     // All rows of this warp are loaded before any is processed: the flush is a latency chain otherwise (LDS -> test -> RED).
@@ -226,6 +238,7 @@ __device__ __forceinline__ void flush_box(int* __restrict__ gb, const GradMeta& 
         const int tx = gm.bx0 + 4 * x4;
         const bool col_ok = (unsigned)tx < (unsigned)Wt;          // bx0 % 4 == 0 and Wt % 4 == 0: a quad is inside or outside as a whole
         float* d = (ch == 0 ? dst[0] : ch == 1 ? dst[1] : ch == 2 ? dst[2] : dst[3]) + tx;
+        const float sc = ch < 3 ? gm.scale_rgb : gm.scale;
 #pragma unroll
         for (int k = 0; k < kRowsPerWarp; ++k) {
             const int r = fw + k * kBwdFlushWarps;
@@ -251,7 +264,7 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
     __shared__ GradMeta s_gmeta[kBwdBoxes];
     __shared__ __align__(8) uint64_t s_full[kBwdStages], s_empty[kBwdStages], g_full[kBwdBoxes], g_empty[kBwdBoxes];
     __shared__ TileWalk s_walk;
-    __shared__ unsigned s_qmax[3];        // per-tile bound (bits of a non-negative float), three slots in rotation
+    __shared__ unsigned s_qmax[3], s_gmax[3];   // per-tile bounds (bits of non-negative floats), three slots in rotation
     __shared__ unsigned s_zmax;           // max_i |z_diff_i| of the current view's plane table
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,6 +279,7 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
             mbar_init(&g_empty[s], kBwdFlushWarps);
         }
         s_qmax[0] = s_qmax[1] = s_qmax[2] = 0u;
+        s_gmax[0] = s_gmax[1] = s_gmax[2] = 0u;
         s_zmax = 0u;
         fence_mbar_init();
     }
@@ -290,7 +304,8 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                 const int b = f_box;
                 const uint32_t ph = f_phase;
                 if (++f_box == kBwdBoxes) { f_box = 0; f_phase ^= 1u; }
-                mbar_wait_sleep(&g_full[b], ph);
+                if (BwdRing::kSleepPolls) mbar_wait_sleep(&g_full[b], ph);
+                else mbar_wait(&g_full[b], ph);
                 const GradMeta gm = s_gmeta[b];
                 int* gb = s_grad + b * kBwdPlaneFloats;
                 if (gm.rows > 0) {
@@ -309,7 +324,9 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
     } else {
         // ================================ consumers ================================
         const float fWt = (float)Wt, fHt = (float)Ht;
-        const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+        float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+        int lane_ = lane;
+        asm volatile("" : "+f"(hsx), "+f"(hsy), "+r"(lane_));     // opaque: not re-derived from the parameters in every plane iteration
         const size_t img = (size_t)p.H * p.W;
         int c_stage = 0, g_box = 0;
         uint32_t c_phase = 0, g_phase = 0;
@@ -344,7 +361,7 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
             float gq[kPix][4];
             bool rays_fast = (in_safe_range(ev[0]) || ev[0] == 0.0f) && (in_safe_range(ev[1]) || ev[1] == 0.0f);
             const float zmax = __uint_as_float(s_zmax);
-            float qmax = 0.0f;
+            float qmax = 0.0f, gmax = 0.0f;
 #pragma unroll
             for (int q = 0; q < kPix; ++q) {
                 const int pxq = px0 + lane + 32 * (q & 1), pyq = py0 + kPairs * warp + (q >> 1);
@@ -359,20 +376,29 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                 gq[q][2] = valid ? gscale * __ldg(gc + 2 * img) : 0.0f;
                 gq[q][3] = (valid && p.g_depth) ? __ldg(p.g_depth + (size_t)v * img + pix) * rc[q].dz : 0.0f;
                 qmax = fmaxf(qmax, fabsf(gq[q][0]) + fabsf(gq[q][1]) + fabsf(gq[q][2]) + fabsf(gq[q][3]) * (zmax * fabsf(rc[q].yrz)));
+                gmax = fmaxf(gmax, fmaxf(fabsf(gq[q][0]), fmaxf(fabsf(gq[q][1]), fabsf(gq[q][2]))));
             }
             // ---- the tile's fixed-point scale: max over all consumer threads (three slots in rotation, see below) ----
             {
                 const int slot = j % 3;
-                for (int o = 16; o > 0; o >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
-                if (!(qmax < 0x1p100f)) qmax = 0x1p100f;             // inf/NaN upstream gradients: keep the exponent finite
-                if (lane == 0) atomicMax(&s_qmax[slot], __float_as_uint(qmax));
-                if (threadIdx.x == 0) s_qmax[(j + 1) % 3] = 0u;       // next tile's slot: its last readers passed the previous tile's barrier
+                for (int o = 16; o > 0; o >>= 1) {
+                    qmax = fmaxf(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+                    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+                }
+                if (!(qmax < 0x1p100f)) qmax = 0x1p100f;             // inf/NaN upstream gradients: keep the exponents finite
+                if (!(gmax < 0x1p100f)) gmax = 0x1p100f;
+                if (lane == 0) { atomicMax(&s_qmax[slot], __float_as_uint(qmax)); atomicMax(&s_gmax[slot], __float_as_uint(gmax)); }
+                if (threadIdx.x == 0) s_qmax[(j + 1) % 3] = s_gmax[(j + 1) % 3] = 0u;   // next tile's slots: their last readers passed the previous tile's barrier
                 bwd_consumer_bar_sync();
                 qmax = __uint_as_float(s_qmax[slot]);
+                gmax = __uint_as_float(s_gmax[slot]);
             }
             const int e_fix = tile_scale_exponent(qmax);
             const f2 Fs = splat(__uint_as_float((unsigned)(127 + kFixBits - e_fix) << 23));      // 2^(kFixBits - e)
             const float inv_scale = __uint_as_float((unsigned)(127 - kFixBits + e_fix) << 23);    // 2^(e - kFixBits)
+            const int e_rgb = tile_scale_exponent(0.5f * gmax);                                   // 2^e_rgb > 2 gmax
+            const f2 Fs_rgb = splat(__uint_as_float((unsigned)(127 + kFixBitsRgb - e_rgb) << 23));
+            const float inv_scale_rgb = __uint_as_float((unsigned)(127 - kFixBitsRgb + e_rgb) << 23);
 
             const bool idle = py0 + kPairs * warp >= p.H;      // warp-uniform: no row of this warp is inside the image
 #pragma unroll
@@ -410,27 +436,21 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                     const float* tr = sb + kBwdPlaneFloats + (kPairs * warp + P) * kTileW + lane;
                     T[P] = make_float2(tr[0], tr[32]);
                 }
-                int idx[kPix], jdx[kPix];
-                f2 w4[kPairs][4], val[kPairs][4];
-                constexpr int AO = kFactored ? kBwdAlphaOff : 0;
-                int cls = -1;
-                if (warp_fast) {   // warp-uniform, one-hot class
-                    if (sel & (1 << 18)) cls = bwd_box_pairs<72, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 2 : -1;
-                    else if (sel & (1 << 17)) cls = bwd_box_pairs<64, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 1 : -1;
-                    else if (sel & (1 << 19)) cls = bwd_box_pairs<80, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 3 : -1;
-                    else if (sel & (1 << 16)) cls = bwd_box_pairs<56, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 0 : -1;
-                    else if (sel & (1 << 20)) cls = bwd_box_pairs<88, AO>(sb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, idx, jdx, w4, val) ? 4 : -1;
-                }
-                __syncwarp();
-                mbar_arrive_if(&s_empty[s], lane == 0);     // taps and transmittance are in registers: hand the stage back
-                // ---- gradient box of this (tile, plane): wait until the flushers have emptied it ----
+                // ---- gradient box of this (tile, plane): wait until the flushers have emptied it, then sample and scatter ----
                 mbar_wait(&g_empty[b], gph ^ 1u);
                 int* gb = s_grad + b * kBwdPlaneFloats;
-                if (cls == 2) box_scatter<72, AO>(gb, idx, jdx, w4, val, Fs);
-                else if (cls == 1) box_scatter<64, AO>(gb, idx, jdx, w4, val, Fs);
-                else if (cls == 3) box_scatter<80, AO>(gb, idx, jdx, w4, val, Fs);
-                else if (cls == 0) box_scatter<56, AO>(gb, idx, jdx, w4, val, Fs);
-                else if (cls == 4) box_scatter<88, AO>(gb, idx, jdx, w4, val, Fs);
+                constexpr int AO = kFactored ? kBwdAlphaOff : 0;
+                bool done = false;
+                if (warp_fast) {   // warp-uniform, one-hot class
+                    if (sel & (1 << 18)) done = bwd_box_pairs<72, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
+                    else if (sel & (1 << 17)) done = bwd_box_pairs<64, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
+                    else if (sel & (1 << 19)) done = bwd_box_pairs<80, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
+                    else if (sel & (1 << 16)) done = bwd_box_pairs<56, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
+                    else if (sel & (1 << 20)) done = bwd_box_pairs<88, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
+                }
+                const int cls = done ? 0 : -1;
+                __syncwarp();
+                mbar_arrive_if(&s_empty[s], lane_ == 0);    // taps and transmittance are consumed: hand the stage back
                 if (warp == 0 && lane == 0) {               // (warp 0 always has a row inside the image)
                     GradMeta gm;
                     const int mode = (sel >> 8) & 3;
@@ -439,11 +459,12 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                     gm.cls = ((sel & 0xff) - kMinBW) / kBWStep;
                     gm.plane = m * N + i;
                     gm.scale = inv_scale;
-                    gm.mpi = m; gm.bg = (kFactored && p.g_bg_rgb && i == N - 1) ? 1 : 0;
+                    gm.scale_rgb = inv_scale_rgb;
+                    gm.mpi_bg = 2 * m + ((kFactored && p.g_bg_rgb && i == N - 1) ? 1 : 0);
                     s_gmeta[b] = gm;
                 }
                 __syncwarp();
-                mbar_arrive_if(&g_full[b], lane == 0);
+                mbar_arrive_if(&g_full[b], lane_ == 0);
                 if (cls < 0 && !idle) {
                     // ---- generic body (rare): per-pixel checks, sampling and scattering straight in global memory.  Also
                     // taken when the producer's corner-ray estimate says "nothing under the tile": a hint, never trusted ----

@@ -291,6 +291,10 @@ struct FwdRing {
     static constexpr int kPlaneFloats = kStageFloats;      // floats of one staged plane box
     static constexpr int kStride = kStageFloats;           // floats per ring stage
     static constexpr bool kReverse = false;                // planes front to back; no transmittance box
+#ifndef GMPI_FWD_SLEEP
+#define GMPI_FWD_SLEEP 0      // measured: sleeping between polls costs the forward 1 % (the 3-stage ring wants its producer prompt)
+#endif
+    static constexpr bool kSleepPolls = GMPI_FWD_SLEEP != 0;   // producer sleeps between polls of a full ring (see mbar_wait_sleep)
 };
 // factored MPI: the colour box [row][3][bw] starts the stage, the alpha box [row][bw] follows at this offset (floats)
 constexpr int kFwdAlphaOff = 3 * kMaxBW * kMaxBH;
@@ -348,7 +352,8 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             const int bw = kMinBW + k * kBWStep;
             const int n_ops = mode == 0 ? (need_h + kRowsPerOp - 1) / kRowsPerOp : 0;
             const int rows = n_ops * kRowsPerOp;
-            mbar_wait_sleep(&s_empty[s], ph ^ 1);
+            if (Ring::kSleepPolls) mbar_wait_sleep(&s_empty[s], ph ^ 1);
+            else mbar_wait(&s_empty[s], ph ^ 1);
             if (lane == 0) {
                 StageMeta mt;
                 mt.cx = kFloorMagicBits + bx0; mt.cy = kFloorMagicBits + by0;
@@ -399,32 +404,32 @@ __device__ __forceinline__ void quad_transpose(float (&a)[4], int lane) {
 //   * float4 stores after a quad transpose (lane k of a quad ends up with channel k of four consecutive x): 4 x STG.128 per
 //     thread instead of 16 x STG.32 -- and 4 per peer in the fused all-gather, or 4 in total through a multicast address;
 //   * the scalar store_pixel path for odd widths / unaligned outputs.
-__device__ __forceinline__ void store_tile_rows(const RenderParams& p, int v, size_t img, int px0, int py, int lane, float (&out)[kPix][4]) {
-    if (p.options & kOptVec4Stores) {
-        const int k = lane & 3, xq = 4 * (lane >> 2);
-#pragma unroll
-        for (int q = 0; q < kPix; ++q) {
-            quad_transpose(out[q], lane);          // all lanes take part, whatever their bounds
-            const int px = px0 + 32 * (q & 1) + xq, pyq = py + (q >> 1);
-            if (px >= p.W || pyq >= p.H) continue;  // W % 4 == 0: a quad is inside or outside as a whole
-            const float4 val = make_float4(out[q][0], out[q][1], out[q][2], out[q][3]);
-            const size_t pix = (size_t)pyq * p.W + px;
-            if (p.n_peers > 0) {
-                const size_t fo = ((size_t)(p.frame_offset + v) * 4 + k) * img + pix;
-                for (int r = 0; r < p.n_peers; ++r) *reinterpret_cast<float4*>(p.peer_frames[r] + fo) = val;
-            } else {
-                float* dst = k < 3 ? p.color + ((size_t)v * 3 + k) * img + pix : p.depth + (size_t)v * img + pix;
-                *reinterpret_cast<float4*>(dst) = val;
-            }
+// Epilogue of one consumer warp, one pixel set at a time: o = (R, G, B, depth) of pixel (pxb + lane, py) of view v; all 32 lanes
+// call this (the quad transpose shuffles).  Destinations:
+//   * float4 stores after a quad transpose (lane k of a quad ends up with channel k of four consecutive x): 4 x STG.128 per
+//     thread and tile instead of 16 x STG.32 -- and 4 per peer in the fused all-gather, or 4 in total through a multicast address;
+//   * store_pixel for odd widths / unaligned outputs and for the uint8 video frames (render_video.py:118-126).
+// (Collecting the four pixel sets in a [4][4] array first costs the plane loop 8 instructions per iteration through register
+// pressure -- measured: -5 % frames/s -- so each set is stored as soon as it is formed.)
+__device__ __forceinline__ void store_tile_pixels(const RenderParams& p, int v, size_t img, int pxb, int py, int lane, float (&o)[4]) {
+    if (p.options & kOptVec4Stores) {      // (never set together with the video outputs)
+        quad_transpose(o, lane);               // lane k of a quad now holds channel k of four consecutive x
+        const int k = lane & 3, px = pxb + 4 * (lane >> 2);
+        if (px >= p.W || py >= p.H) return;     // W % 4 == 0: a quad is inside or outside as a whole
+        const float4 val = make_float4(o[0], o[1], o[2], o[3]);
+        const size_t pix = (size_t)py * p.W + px;
+        if (p.n_peers > 0) {
+            const size_t fo = ((size_t)(p.frame_offset + v) * 4 + k) * img + pix;
+            for (int r = 0; r < p.n_peers; ++r) *reinterpret_cast<float4*>(p.peer_frames[r] + fo) = val;
+        } else {
+            float* dst = k < 3 ? p.color + ((size_t)v * 3 + k) * img + pix : p.depth + (size_t)v * img + pix;
+            *reinterpret_cast<float4*>(dst) = val;
         }
         return;
     }
-#pragma unroll
-    for (int q = 0; q < kPix; ++q) {
-        const int px = px0 + lane + 32 * (q & 1), pyq = py + (q >> 1);
-        if (px >= p.W || pyq >= p.H) continue;
-        store_pixel(p, v, img, (size_t)pyq * p.W + px, out[q][0], out[q][1], out[q][2], out[q][3]);
-    }
+    const int px = pxb + lane;
+    if (px >= p.W || py >= p.H) return;
+    store_pixel(p, v, img, (size_t)py * p.W + px, o[0], o[1], o[2], o[3]);
 }
 
 template <bool kAlignCorners, bool kEmitT, bool kFactored>
@@ -450,7 +455,13 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
 
     const int Ht = p.Ht, Wt = p.Wt, N = p.N;
     const float fWt = (float)Wt, fHt = (float)Ht;
-    const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
+    // Opaque to the optimiser: otherwise ptxas, short of registers, re-derives these two constants from the kernel parameters in
+    // EVERY plane iteration (2 x LDCU + UIADD3 + I2FP + FMUL, the I2FP on the XU pipe behind the tap loads' MIO queue) -- seen
+    // in the round-2 profile after unrelated prologue/epilogue changes: +3 % kernel time.
+    asm volatile("" : "+f"(hsx), "+f"(hsy));
+    int lane_ = lane;
+    asm volatile("" : "+r"(lane_));     // likewise: no S2R + LOP3 per plane for the `lane == 0` of the arrive
     const size_t img = (size_t)p.H * p.W;
 
     if (warp == kConsWarps) {
@@ -587,7 +598,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     }
                 }
                 __syncwarp();
-                mbar_arrive_if(&s_empty[s], lane == 0);     // predicated, no branch
+                mbar_arrive_if(&s_empty[s], lane_ == 0);    // predicated, no branch
             }
             if (check_last) {     // assert_not_out_of_last_plane, mpi.py:103-109 (once per tile)
                 const PlaneConst pcl = s_pc[N - 1];
@@ -599,19 +610,18 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     if (!(tc.u >= -1.0f && tc.u <= 1.0f && tc.v >= -1.0f && tc.v <= 1.0f)) flag |= GMPI_FLAG_LAST_PLANE_OOB;
                 }
             }
-            // ---- epilogue: the warp's 2 rows x 64 pixels, (R, G, B, depth) per pixel ----
-            float out[kPix][4];
+            // ---- epilogue: the warp's 2 rows x 64 pixels, (R, G, B, depth) per pixel, one pixel set at a time ----
 #pragma unroll
             for (int q = 0; q < kPix; ++q) {
-                float o0 = (q & 1) ? cr[q >> 1].y : cr[q >> 1].x, o1 = (q & 1) ? cg[q >> 1].y : cg[q >> 1].x;
-                float o2 = (q & 1) ? cb[q >> 1].y : cb[q >> 1].x;
-                const float ws = (q & 1) ? cws[q >> 1].y : cws[q >> 1].x;
+                float o[4];
+                o[0] = (q & 1) ? cr[q >> 1].y : cr[q >> 1].x; o[1] = (q & 1) ? cg[q >> 1].y : cg[q >> 1].x;
+                o[2] = (q & 1) ? cb[q >> 1].y : cb[q >> 1].x;
+                o[3] = ((q & 1) ? cws[q >> 1].y : cws[q >> 1].x) * rc[q].dz;
                 if (minus1_1) {
-                    o0 = fmaf(2.0f, o0, -1.0f); o1 = fmaf(2.0f, o1, -1.0f); o2 = fmaf(2.0f, o2, -1.0f);
+                    o[0] = fmaf(2.0f, o[0], -1.0f); o[1] = fmaf(2.0f, o[1], -1.0f); o[2] = fmaf(2.0f, o[2], -1.0f);
                 }
-                out[q][0] = o0; out[q][1] = o1; out[q][2] = o2; out[q][3] = ws * rc[q].dz;
+                store_tile_pixels(p, v, img, px0 + 32 * (q & 1), py0 + kPairs * warp + (q >> 1), lane, o);
             }
-            store_tile_rows(p, v, img, px0, py0 + kPairs * warp, lane, out);
         }
         if (flag) atomicOr(p.flags, flag);
     }

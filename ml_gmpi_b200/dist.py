@@ -71,20 +71,29 @@ class FrameGather:
     per step with a reader in flight to cover this.)
     """
 
-    def __init__(self, frames_per_rank: int, H: int, W: int, device, group=None):
+    def __init__(self, frames_per_rank: int, H: int, W: int, device, group=None, multicast="auto"):
+        """multicast: "auto" (use the NVLS multicast mapping of the buffers when the fabric offers one), True (require it), False
+        (per-peer stores).  With a multicast address the epilogue issues ONE float4 store per quad and the NVSwitch replicates it
+        to every rank's buffer; without, n_peers stores."""
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.frames_per_rank, self.H, self.W = frames_per_rank, H, W
         self._bufs, self._handles, self._peer_ptrs = [], [], []
+        self.multicast = False
         for _ in range(2):
             buf = symm_mem.empty((self.world * frames_per_rank, 4, H, W), dtype=torch.float32, device=device)
             handle = symm_mem.rendezvous(buf, self.group)
             ptrs = [int(p) for p in handle.buffer_ptrs]
             assert len(ptrs) == self.world
+            mc = int(getattr(handle, "multicast_ptr", 0) or 0)
+            if multicast is True and mc == 0:
+                raise RuntimeError("FrameGather(multicast=True): the symmetric-memory handle has no multicast mapping (no NVLS)")
+            if multicast and mc != 0:
+                ptrs, self.multicast = [mc], True
             self._bufs.append(buf)
             self._handles.append(handle)
-            self._peer_ptrs.append(torch.tensor(ptrs, dtype=torch.int64, device=device))   # device array of float* (one per rank)
+            self._peer_ptrs.append(torch.tensor(ptrs, dtype=torch.int64, device=device))   # device array of float* (peers, or the multicast address)
         self._next, self._done = 0, None
 
     @property
@@ -105,7 +114,8 @@ class FrameGather:
         with torch.cuda.device(rgba.device):
             _lib.check(lib.gmpi_mpi_render_fwd_gather(
                 rgba.data_ptr(), view2mpi.data_ptr(), dhw.data_ptr(), ray_dir.data_ptr(), eye.data_ptr(), z_dir.data_ptr(),
-                self._peer_ptrs[self._next].data_ptr(), self.world, self.rank * self.frames_per_rank, flags.data_ptr(),
+                self._peer_ptrs[self._next].data_ptr(), int(self._peer_ptrs[self._next].numel()), self.rank * self.frames_per_rank,
+                flags.data_ptr(),
                 M, V, N, Ht, Wt, self.H, self.W, options, torch.cuda.current_stream(rgba.device).cuda_stream))
 
     def finish(self):

@@ -220,7 +220,12 @@ def test_video_service_equals_the_per_view_reference_loop():
         im, dm, _, _ = r.render(mpi, I, I, horizontal_mean=a, horizontal_std=0.0, vertical_mean=0.0, vertical_std=0.0,
                                 assert_not_out_of_last_plane=True)
         ref_img, ref_depth = _video_reference(im, dm, near, far)
-        assert np.array_equal(img[i].numpy(), ref_img[0]) and np.array_equal(depth[i].numpy(), ref_depth[0]), i
+        # The service rotates the camera rays of all its views in ONE batched matmul, the loop one view at a time: cuBLAS may sum
+        # the three products in a different order, the rays differ in the last ulp and a white-noise MPI turns that into a grey
+        # level on a few pixels.  (With identical rays the frames are identical: test_video_epilogue_equals_reference_conversion.)
+        for ours, ref in ((img[i].numpy(), ref_img[0]), (depth[i].numpy(), ref_depth[0])):
+            diff = np.abs(ours.astype(np.int16) - ref.astype(np.int16))
+            assert int(diff.max()) <= 1 and float((diff > 0).mean()) < 0.02, (i, int(diff.max()), float((diff > 0).mean()))
     # the fast mode (rays generated in the kernel) differs from the parity frames by at most one grey level on a few pixels
     fast, _ = service.render_video_frames(mpi, dhw, angles, img_size=I, fov_deg=12.6, ray_start=near, ray_end=far,
                                           sphere_center=r.sphere_center, sphere_r=r.sphere_r, fast_rays=True)

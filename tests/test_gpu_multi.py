@@ -29,7 +29,18 @@ def _worker(rank, world, port, q):
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         color, depth = g.render_views(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, color_minus1_1=True)
         ref = gdist.all_gather_frames(gdist.pack_frames(color, depth))              # NCCL path
-        fg = gdist.FrameGather(B, R, R, dev)
+        # NVLS multicast variant (one store per quad, the switch replicates), when the fabric has it
+        mc_ok = None
+        try:
+            fgm = gdist.FrameGather(B, R, R, dev, multicast=True)
+        except RuntimeError:
+            fgm = None
+        if fgm is not None:
+            fgm.render(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, flags, color_minus1_1=True)
+            fgm.finish()
+            torch.cuda.synchronize(dev)
+            mc_ok = bool(torch.equal(fgm.frames, ref))
+        fg = gdist.FrameGather(B, R, R, dev, multicast=False)
         for _ in range(2):                                                          # twice: buffers are reused
             fg.render(case.rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir, flags, color_minus1_1=True)
             fg.finish()
@@ -59,7 +70,7 @@ def _worker(rank, world, port, q):
             if not torch.equal(snap, refs[k % 2]):
                 ok = False
                 maxdiff = max(maxdiff, float((snap - refs[k % 2]).abs().max()))
-        q.put((rank, ok, maxdiff, int(flags.item())))
+        q.put((rank, ok and mc_ok is not False, maxdiff, int(flags.item()), mc_ok))
     finally:
         dist.destroy_process_group()
 
@@ -77,5 +88,6 @@ def test_fused_gather_equals_nccl_all_gather():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, equal, maxdiff, fl in res:
-        assert equal and fl == 0, (rank, equal, maxdiff, fl)
+    for rank, equal, maxdiff, fl, mc_ok in res:
+        assert equal and fl == 0, (rank, equal, maxdiff, fl, mc_ok)
+    print("multicast (NVLS) variant:", {r[0]: r[4] for r in res})
