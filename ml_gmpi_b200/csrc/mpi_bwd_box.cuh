@@ -75,6 +75,21 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // Scatter one pixel's four channel gradients through its bilinear footprint straight into global memory
 // (grid_sampler_2d_backward); the rare path of a warp whose footprints are not all inside the staged box.
+// (The expanded instantiation passes one base pointer -- see sample_plane_direct for why -- the factored one four.)
+__device__ __noinline__ void scatter_plane_global(float* __restrict__ gplane, size_t tex, int Wt, int Ht, int x0, int y0, float v0, float v1,
+                                                  float v2, float v3, float w00, float w01, float w10, float w11) {
+    const bool vx0 = (unsigned)x0 < (unsigned)Wt, vx1 = (unsigned)(x0 + 1) < (unsigned)Wt;
+    const bool vy0 = (unsigned)y0 < (unsigned)Ht, vy1 = (unsigned)(y0 + 1) < (unsigned)Ht;
+    float* b0 = gplane + ((long long)y0 * Wt + x0);
+    const float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int c = 0; c < 4; ++c, b0 += tex) {
+        if (vx0 && vy0) red_add(b0, v[c] * w00);
+        if (vx1 && vy0) red_add(b0 + 1, v[c] * w01);
+        if (vx0 && vy1) red_add(b0 + Wt, v[c] * w10);
+        if (vx1 && vy1) red_add(b0 + Wt + 1, v[c] * w11);
+    }
+}
 __device__ __noinline__ void scatter_pixel_global(const GradChans gch, int Wt, int Ht, int x0, int y0, float v0, float v1,
                                                   float v2, float v3, float w00, float w01, float w10, float w11) {
     const bool vx0 = (unsigned)x0 < (unsigned)Wt, vx1 = (unsigned)(x0 + 1) < (unsigned)Wt;
@@ -103,8 +118,9 @@ __device__ __noinline__ void scatter_pixel_global(const GradChans gch, int Wt, i
 constexpr int kFixBits = 26, kFixSplit = 4;              // alpha: low kFixSplit bits come from the second conversion step
 // The three colour channels have their own, tighter bound -- |dL/d rgb contribution| = |G_c| a T w <= gmax = max |G_c| over the
 // tile, without the depth term and the factor 2 of the alpha bound -- and take the one-step conversion: 2^e_rgb > 2 gmax,
-// contributions rounded to multiples of 2^(e_rgb - 21) (|c| 2^(21 - e_rgb) < 2^20, far inside the 2^22 the magic constant allows).
-constexpr int kFixBitsRgb = 21;
+// contributions rounded to multiples of 2^(e_rgb - 22) (|c| 2^(22 - e_rgb) < 2^21: a factor 2 inside the 2^22 the magic constant
+// allows, for inputs that leave [0,1] by rounding).
+constexpr int kFixBitsRgb = 22;
 constexpr float kMagicHi = 12582912.0f * 16.0f;          // 1.5 * 2^(23 + kFixSplit): ulp = 2^kFixSplit
 constexpr int kMagicHiBits = 0x4b400000 + (kFixSplit << 23);
 __device__ __forceinline__ int tile_scale_exponent(float qmax) {
@@ -292,7 +308,7 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
     if (warp == kBwdConsWarps) {
         // ================================ producer ================================
         if (lane == 0) tma_prefetch_desc(&maps.t);
-        staged_producer<kAlignCorners, BwdRing>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
+        staged_producer<kAlignCorners, BwdRing, kFactored>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
     } else if (warp > kBwdConsWarps) {
         // ================================ flushers ================================
         const int fw = warp - kBwdConsWarps - 1;
@@ -468,8 +484,8 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                 if (cls < 0 && !idle) {
                     // ---- generic body (rare): per-pixel checks, sampling and scattering straight in global memory.  Also
                     // taken when the producer's corner-ray estimate says "nothing under the tile": a hint, never trusted ----
-                    const PlaneChans plane = plane_chans(p, m, i, tex);
-                    const GradChans gplane = grad_chans(p, m, i, tex);
+                    const float* plane = kFactored ? nullptr : p.rgba + ((size_t)m * N + i) * 4 * tex;
+                    float* gplane = kFactored ? nullptr : p.g_rgba + ((size_t)m * N + i) * 4 * tex;
                     float* Rs = reinterpret_cast<float*>(R);
                     const float* Ts = reinterpret_cast<const float*>(T);
 #pragma unroll
@@ -479,15 +495,19 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                         rg.fast = false;
                         const TexCoord tc = plane_coord<kAlignCorners>(pcc, rg, hsx, hsy, fWt, fHt);
                         if (!coord_hits(tc.ix, tc.iy, fWt, fHt)) continue;
-                        const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
+                        const float4 sv = sample_plane_any<kFactored>(p, plane, m, i, tex, tc.ix, tc.iy);
                         const float fx = floorf(tc.ix), fy = floorf(tc.iy);
                         const float wx1 = tc.ix - fx, wy1 = tc.iy - fy, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
                         const float qv = fmaf(gq[q][0], sv.x, fmaf(gq[q][1], sv.y, fmaf(gq[q][2], sv.z, gq[q][3] * tc.scale)));
                         const float d = qv - Rs[qq];
                         const float w = sv.w * Ts[qq];
                         Rs[qq] = fmaf(sv.w, d, Rs[qq]);
-                        scatter_pixel_global(gplane, Wt, Ht, (int)fx, (int)fy, gq[q][0] * w, gq[q][1] * w, gq[q][2] * w, Ts[qq] * d,
-                                             wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
+                        if (kFactored)
+                            scatter_pixel_global(grad_chans(p, m, i, tex), Wt, Ht, (int)fx, (int)fy, gq[q][0] * w, gq[q][1] * w, gq[q][2] * w,
+                                                 Ts[qq] * d, wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
+                        else
+                            scatter_plane_global(gplane, tex, Wt, Ht, (int)fx, (int)fy, gq[q][0] * w, gq[q][1] * w, gq[q][2] * w, Ts[qq] * d,
+                                                 wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1);
                     }
                 }
             }

@@ -101,7 +101,8 @@ __device__ __forceinline__ void cam_ray(const float* __restrict__ cam, int px, i
 __device__ __forceinline__ void load_ray(const RenderParams& p, int v, int px, int py, size_t img, float& rx, float& ry, float& rz) {
     if (p.cam) {
         cam_ray(p.cam + 16 * (size_t)v, px, py, p.H, p.W, rx, ry, rz);
-    } else {
+    } else
+    {
         const float* rd = p.ray_dir + (size_t)v * 3 * img + (size_t)py * p.W + px;
         rx = __ldg(rd); ry = __ldg(rd + img); rz = __ldg(rd + 2 * img);
     }
@@ -112,7 +113,8 @@ __device__ __forceinline__ void load_eye_z(const RenderParams& p, int v, float (
         const float* c = p.cam + 16 * (size_t)v;
         ev[0] = __ldg(c + 13); ev[1] = __ldg(c + 14); ev[2] = __ldg(c + 15);
         zd[0] = __ldg(c + 6); zd[1] = __ldg(c + 9); zd[2] = __ldg(c + 12);     // R[:, 2]
-    } else {
+    } else
+    {
         ev[0] = __ldg(p.eye + 3 * v); ev[1] = __ldg(p.eye + 3 * v + 1); ev[2] = __ldg(p.eye + 3 * v + 2);
         zd[0] = __ldg(p.z_dir + 3 * v); zd[1] = __ldg(p.z_dir + 3 * v + 1); zd[2] = __ldg(p.z_dir + 3 * v + 2);
     }

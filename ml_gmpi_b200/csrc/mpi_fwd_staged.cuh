@@ -124,7 +124,8 @@ __device__ __forceinline__ void coords_pairs(const PlaneConst& pc, const RayPair
         const f2 sq = div2_by_rcp(zd, rp.nrz[P], rp.yrz[P]);                 // scale = z_diff / ray_z
         // 2*(e_x + ray_x*scale): mul, THEN add (two roundings, mpi.py:79).  Scalar on purpose: ptxas fuses
         // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in SASS even with --fmad=false), which is not the reference's
-        // arithmetic; the scalar __fmul_rn/__fadd_rn intrinsics are never contracted.
+        // arithmetic; the scalar __fmul_rn/__fadd_rn intrinsics are never contracted.  (Writing the add as fma(p, 1, e) does not
+        // help either: ptxas folds the multiplication by one and contracts again -- caught by the output checksum, round 2.)
         const f2 X2 = make_float2(__fadd_rn(ex2.x, __fmul_rn(rp.rx2[P].x, sq.x)), __fadd_rn(ex2.y, __fmul_rn(rp.rx2[P].y, sq.y)));
         const f2 Y2 = make_float2(__fadd_rn(ey2.x, __fmul_rn(rp.ry2[P].x, sq.x)), __fadd_rn(ey2.y, __fmul_rn(rp.ry2[P].y, sq.y)));
         f2 u = div2_by_rcp(X2, npw, ypw);                                    // (2x) / width
@@ -208,9 +209,23 @@ __device__ __forceinline__ bool sample_pairs(const float* __restrict__ sb, int c
 
 // Rare path (a ray whose footprint is not in the staged box): sample the plane from global memory.  Out of line so
 // that it does not cost registers in the hot loop.
-__device__ __noinline__ float4 sample_plane_direct(const PlaneChans pl, int Ht, int Wt, float ix, float iy) {
+// Expanded MPI: ONE base pointer crosses the call.  (Passing the four channel pointers of PlaneChans instead -- 8 registers that
+// are live only inside the rare branch -- still shifted the register allocation of the hot loop: -3.8 % frames/s, bisected on
+// the GPU in round 2.  The factored instantiation, which needs them, is a separate template instance.)
+__device__ __noinline__ float4 sample_plane_direct(const float* __restrict__ plane, int Ht, int Wt, float ix, float iy) {
+    const size_t tex = (size_t)Ht * Wt;
+    const Taps tp = make_taps(ix, iy, Ht, Wt);
+    return make_float4(tap4(plane, tp), tap4(plane + tex, tp), tap4(plane + 2 * tex, tp), tap4(plane + 3 * tex, tp));
+}
+__device__ __noinline__ float4 sample_chans_direct(const PlaneChans pl, int Ht, int Wt, float ix, float iy) {
     const Taps tp = make_taps(ix, iy, Ht, Wt);
     return make_float4(tap4(pl.c[0], tp), tap4(pl.c[1], tp), tap4(pl.c[2], tp), tap4(pl.c[3], tp));
+}
+// generic-path sample of plane i of MPI m: the instantiation decides which form crosses the call
+template <bool kFactored>
+__device__ __forceinline__ float4 sample_plane_any(const RenderParams& p, const float* plane, int m, int i, size_t tex, float ix, float iy) {
+    if (kFactored) return sample_chans_direct(plane_chans(p, m, i, tex), p.Ht, p.Wt, ix, iy);
+    return sample_plane_direct(plane, p.Ht, p.Wt, ix, iy);
 }
 
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
@@ -299,7 +314,9 @@ struct FwdRing {
 // factored MPI: the colour box [row][3][bw] starts the stage, the alpha box [row][bw] follows at this offset (floats)
 constexpr int kFwdAlphaOff = 3 * kMaxBW * kMaxBH;
 
-template <bool kAlignCorners, class Ring>
+// kFact: factored MPI (compile time: a run-time test of p.alpha in this loop cost the forward 1 %, the producer's per-stage latency
+// being on the critical path of a three-stage ring).
+template <bool kAlignCorners, class Ring, bool kFact>
 __device__ __forceinline__ void staged_producer(const RenderParams& p, const TmaMaps& maps, float* s_buf, StageMeta* s_meta,
                                             uint64_t* s_full, uint64_t* s_empty, const TileWalk* s_walk, int lane) {
     constexpr bool kReverse = Ring::kReverse;
@@ -311,7 +328,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
     const float hsx = 0.5f * (float)(Wt - 1), hsy = 0.5f * (float)(Ht - 1);
     const size_t img = (size_t)p.H * p.W;
     if (lane < kNumMaps) {
-        if (p.alpha) { tma_prefetch_desc(&maps.rgb[lane]); tma_prefetch_desc(&maps.a[lane]); }
+        if (kFact) { tma_prefetch_desc(&maps.rgb[lane]); tma_prefetch_desc(&maps.a[lane]); }
         else tma_prefetch_desc(&maps.m[lane]);
     }
     int p_stage = 0;
@@ -367,7 +384,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             }
             __syncwarp();
             if (lane < n_ops) {
-                if (p.alpha) {       // factored MPI: shared colour (or the last plane's own) + this plane's alpha, two boxes
+                if (kFact) {         // factored MPI: shared colour (or the last plane's own) + this plane's alpha, two boxes
                     float* stage = s_buf + (size_t)s * kStride;
                     const CUtensorMap* cmap = (p.bg_rgb && i == N - 1) ? &maps.bg[k] : &maps.rgb[k];
                     tma_load_4d(stage + (size_t)lane * kRowsPerOp * 3 * bw, cmap, &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m);
@@ -465,7 +482,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const size_t img = (size_t)p.H * p.W;
 
     if (warp == kConsWarps) {
-        staged_producer<kAlignCorners, FwdRing>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
+        staged_producer<kAlignCorners, FwdRing, kFactored>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
     } else {
         // ================================ consumer warps ================================
         // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them
@@ -558,7 +575,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                     const int bw = mt.sel & 0xff, mode = (mt.sel >> 8) & 3, bw4 = 4 * bw;
                     const float fbw2 = (float)(bw - 2), fbh2 = (float)mt.rows2;
                     const float fbx0 = (float)(mt.cx - kFloorMagicBits), fby0 = (float)(mt.cy - kFloorMagicBits);
-                    const PlaneChans plane = plane_chans(p, m, i, tex);
+                    const float* plane = kFactored ? nullptr : p.rgba + ((size_t)m * N + i) * 4 * tex;
                     float* Ts = reinterpret_cast<float*>(T);
                     float* crs = reinterpret_cast<float*>(cr);
                     float* cgs = reinterpret_cast<float*>(cg);
@@ -584,7 +601,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                             a = fmaf(t1[3 * bw + 1], w11, fmaf(t1[3 * bw], w10, fmaf(t0[3 * bw + 1], w01, t0[3 * bw] * w00)));
                         } else if (coord_hits(tc.ix, tc.iy, fWt, fHt)) {   // mode 1 ("nothing under the tile") is only the
                             // producer's corner-ray estimate: every pixel is still tested on its own
-                            const float4 sv = sample_plane_direct(plane, Ht, Wt, tc.ix, tc.iy);
+                            const float4 sv = sample_plane_any<kFactored>(p, plane, m, i, tex, tc.ix, tc.iy);
                             r = sv.x; g = sv.y; b = sv.z; a = sv.w;
                         } else {
                             continue;   // no texel under this ray on this plane: contributes exactly nothing

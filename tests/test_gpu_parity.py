@@ -465,3 +465,25 @@ def test_plan_query_names_the_direct_kernel_cliffs():
     assert lib.gmpi_mpi_render_fwd_plan(4, 96, 1022, 1022, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 1
     assert lib.gmpi_mpi_render_fwd_plan(1, 16, 64, 64, 48, 48, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 2
     assert lib.gmpi_mpi_render_fwd_plan(4, 600, 1024, 1024, 1024, 1024, None, ctypes.byref(why)) == _lib.PLAN_DIRECT and why.value & 4
+
+
+def test_backward_twice_and_interleaved_graphs_use_fresh_gradient_buffers():
+    """The gradient buffers are allocated and zeroed (side stream) during the forward; a second backward through the same node
+    (retain_graph) and two graphs alive at once must not share or re-use them."""
+    from ml_gmpi_b200 import synth
+    d = dev()
+    case = synth.make_case(n_planes=16, tex=256, img=256, n_mpi=2, views_per_mpi=2, seed=31, device=d, last_alpha_one=True)
+    rgba = case.rgba.clone().requires_grad_(True)
+    c1, d1 = g.render_views(rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir)
+    c2, d2 = g.render_views(rgba, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir)      # second graph, same leaf
+    (c1.sum() + d1.sum()).backward(retain_graph=True)
+    g1 = rgba.grad.clone()
+    rgba.grad = None
+    (c1.sum() + d1.sum()).backward()                                                                 # same node again
+    g1b = rgba.grad.clone()
+    rgba.grad = None
+    (2 * c2.sum() + 2 * d2.sum()).backward()
+    g2 = rgba.grad.clone()
+    n = lambda t: t.cpu().numpy()
+    assert rel_err(n(g1b), n(g1)) <= 1e-6 and rel_err(n(g2), 2 * n(g1)) <= 1e-6
+    assert float(g1.abs().max()) > 0

@@ -21,6 +21,10 @@ for step in "$@"; do
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('$v', 'fwd', round(d['value'], 1), 'fps', round(d['roofline']['frac'], 4), round(d['roofline']['kernel_ms'], 4), 'ms; train', round(d['train_step']['ms_per_step'], 3), 'ms', round(d['train_step']['roofline_frac'], 4))" | tee -a $OUT/${TAG}_ab.txt; done ;;
+    fwdab)  timeout 300 python tools/fwd_ab.py r02a - minimal scalarepi 2>&1 | tee $OUT/${TAG}_fwdab.txt ;;
+    launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --no-reference-on-gpu > $OUT/${TAG}_launches_bench.log 2>&1; echo "launches rc=$?" ;;
+    multi)  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > $OUT/${TAG}_pytest_multi.log 2>&1; echo "multi pytest rc=$?"; tail -4 $OUT/${TAG}_pytest_multi.log ;;
+    benchn) NG=$(nvidia-smi -L | wc -l); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG --steps 20 --warmup 5 > $OUT/${TAG}_bench_n$NG.json 2> $OUT/${TAG}_bench_n$NG.err; echo "bench n=$NG rc=$?"; tail -c 800 $OUT/${TAG}_bench_n$NG.err; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus $NG --steps 2 --warmup 1 --ref-budget-s 40 > $OUT/${TAG}_ref_n$NG.json 2> $OUT/${TAG}_ref_n$NG.err; echo "ref n=$NG rc=$?" ;;
     *) echo "unknown step $step" ;;
   esac
 done
