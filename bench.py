@@ -188,7 +188,7 @@ def cpu_reference_frames_per_s(steps, warmup, budget_s, planes=N_PLANES, res=RES
     return {"value": 1.0 / t, "sample": sample, "cores": cores, "ms_per_step": t * 1e3, "spread": spread}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -204,7 +204,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -381,6 +381,7 @@ class FakeBackend:
         self.device = torch.device("cpu")
         self.dist_backend = "gloo"
         self.rank = int(os.environ.get("RANK", "0"))
+        print("[fake backend] a library banner on stdout, as NCCL prints one")     # must not reach the real stdout
 
     def init_dist(self):
         import torch.distributed as dist
@@ -791,7 +792,34 @@ def leg_configs(job, args):
     return out
 
 
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout at the first
+    communicator): during the run file descriptor 1 points at stderr, and the line goes to the real stdout at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def close(self):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+
+
 def main(argv=None):
+    out = OneLineStdout()
+    try:
+        return _main(argv, out)
+    finally:
+        out.close()
+
+
+def _main(argv, out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -809,7 +837,7 @@ def main(argv=None):
     ap.add_argument("--fake", action="store_true", help=argparse.SUPPRESS)     # tests/test_bench_flow.py only
     args = ap.parse_args(argv)
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, out)
     args.warmup = max(args.warmup, 3)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -859,7 +887,7 @@ def main(argv=None):
             "clocks": head["clocks"], "e2e": e2e, "gpu_launches": head["launches"], "roofline": head["roofline"], "cpu_baseline": cpu,
             "train_step": train, "configs": configs, "reference_on_gpu": ref_gpu,
         }
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -31,6 +31,8 @@ def _run(world, extra_env=None, extra_args=()):
         assert p.returncode == 0, se[-3000:]
     lines = [l for l in outs[0][0].splitlines() if l.startswith("{")]
     assert len(lines) == 1, outs[0]
+    assert outs[0][0].count("\n") == 1 and outs[0][0].startswith("{"), "stdout must hold the JSON line and nothing else"
+    assert "library banner" in outs[0][1]                                     # ... the banner went to stderr
     assert all(not [l for l in so.splitlines() if l.startswith("{")] for so, _ in outs[1:])     # only rank 0 prints
     return json.loads(lines[0])
 
