@@ -720,6 +720,30 @@ def leg_configs(job, args):
     assert int(flags.item()) == 0
     del case, color, depth
 
+    # N1: the headline shape rendered from the generator's FACTORED output (shared colour + per-plane alpha): same frames, a
+    # quarter of the HBM bytes (the colour image lives in L2) -- the kernel is bound by its shared-memory tap path, so frames/s
+    # barely moves while the DRAM traffic drops (ncu: profiles/README.md)
+    NP, R, B = be.sizes(args.planes, args.res, args.batch)
+    case = be.make_case(n_planes=NP, tex=R, img=R, n_mpi=B, seed=1234 + rank, rgba=False)
+    rgb, alpha = be.make_factored(B, NP, R, 99 + rank)
+    color, depth = be.empty((B, 3, R, R)), be.empty((B, 1, R, R))
+    ms = job.timed(lambda: be.render(case, color, depth, flags, factored=(rgb, alpha)), steps, warmup=3)
+    alg_f = (4 * NP * R * R + 12 * R * R + 16 * R * R) * B
+    out["N1_factored_fwd"] = {"workload": f"{NP} planes, {R}^2, batch {B} per GPU, forward from rgb [B,3,T,T] + alpha [B,N,1,T,T]",
+                              "frames_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "algorithmic_bytes_per_step": alg_f,
+                              "roofline_frac_of_factored_bytes": alg_f / (ms * 1e-3) / 1e9 / peak,
+                              "bytes_vs_expanded": alg_f / (algorithmic_bytes_fwd(NP, R, R, R, R) * B)}
+    assert int(flags.item()) == 0
+    # N3: LightRenderer.compute_depth on the same alpha stack (light_renderer.py:82-100): one streaming pass, 4 B per texel-plane
+    if be.name == "cuda":
+        from ml_gmpi_b200.light import alpha_depth
+        pd = case.dhw[0, :, 0].contiguous()
+        ms_d = job.timed(lambda: alpha_depth(alpha, pd), steps, warmup=3)
+        bytes_d = (4 * NP * R * R + 4 * R * R) * B
+        out["N3_light_compute_depth"] = {"workload": f"alpha [{B},{NP},1,{R},{R}] -> depth [{B},1,{R},{R}]", "ms_per_step": ms_d,
+                                         "gbs": bytes_d / (ms_d * 1e-3) / 1e9, "roofline_frac": bytes_d / (ms_d * 1e-3) / 1e9 / peak}
+    del case, rgb, alpha, color, depth
+
     # C4: video render: ONE 96-plane 512^2 MPI (replicated: every rank regenerates it from the same seed), 120 novel views
     # yaw = linspace(0.5, -0.5, 120) sharded over the ranks, frames all-gathered: strong scaling
     NP, R, _ = be.sizes(96, 512, 1)

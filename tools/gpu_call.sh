@@ -25,6 +25,7 @@ print('$v', 'fwd', round(d['value'], 1), 'fps', round(d['roofline']['frac'], 4),
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --no-reference-on-gpu > $OUT/${TAG}_launches_bench.log 2>&1; echo "launches rc=$?" ;;
     multi)  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > $OUT/${TAG}_pytest_multi.log 2>&1; echo "multi pytest rc=$?"; tail -4 $OUT/${TAG}_pytest_multi.log ;;
     benchn) NG=$(nvidia-smi -L | wc -l); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG --steps 20 --warmup 5 > $OUT/${TAG}_bench_n$NG.json 2> $OUT/${TAG}_bench_n$NG.err; echo "bench n=$NG rc=$?"; tail -c 800 $OUT/${TAG}_bench_n$NG.err; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus $NG --steps 2 --warmup 1 --ref-budget-s 40 > $OUT/${TAG}_ref_n$NG.json 2> $OUT/${TAG}_ref_n$NG.err; echo "ref n=$NG rc=$?" ;;
+    ncuextra) for w in fwdfact c4 c4flat; do timeout 400 ncu --set full --clock-control none -k regex:mpi_fwd_staged -c 1 -o $OUT/${TAG}_prof_$w python tools/run_one.py $w > $OUT/${TAG}_ncu_$w.log 2>&1; echo "ncu $w rc=$?"; done ;;
     *) echo "unknown step $step" ;;
   esac
 done
