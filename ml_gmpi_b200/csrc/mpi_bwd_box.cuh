@@ -30,7 +30,19 @@
 
 namespace gmpi {
 
-constexpr int kBwdConsWarps = 12, kBwdFlushWarps = 3;
+// Build-time tunables, for A/B builds (profiles/README.md, round 2): 11 consumer + 4 flusher warps (64 x 22 tiles) is 1 % faster at
+// 1024^2 and 27 % slower at 512^2; sweeping the box as one linear run of quads (all flusher lanes busy) is 3 % slower; waiting
+// for the emptied gradient box only before the first scatter instead of before the sampling is 2.2 % faster.
+#ifndef GMPI_BWD_CONS_WARPS
+#define GMPI_BWD_CONS_WARPS 12
+#endif
+#ifndef GMPI_BWD_FLUSH_WARPS
+#define GMPI_BWD_FLUSH_WARPS 3
+#endif
+#ifndef GMPI_BWD_LATE_WAIT
+#define GMPI_BWD_LATE_WAIT 1
+#endif
+constexpr int kBwdConsWarps = GMPI_BWD_CONS_WARPS, kBwdFlushWarps = GMPI_BWD_FLUSH_WARPS;
 constexpr int kBwdTileH = kPairs * kBwdConsWarps;                                   // 64 x 24 pixel tiles
 constexpr int kBwdConsThreads = kBwdConsWarps * 32;
 constexpr int kBwdThreads = (kBwdConsWarps + 1 + kBwdFlushWarps) * 32;              // 16 warps: 12 consumers, producer, 3 flushers
@@ -50,6 +62,7 @@ struct BwdRing {
 #define GMPI_BWD_SLEEP 1
 #endif
     static constexpr bool kSleepPolls = GMPI_BWD_SLEEP != 0;
+    static constexpr bool kWideFact = false;     // the backward keeps the 56..88-wide classes: its shared memory is full
 };
 
 struct GradPairs {
@@ -168,7 +181,8 @@ __device__ __forceinline__ void scatter_channel(int* __restrict__ ga, int* __res
 // ~36 registers and spills.
 template <int BW, int AOFF = 0>
 __device__ __forceinline__ bool bwd_box_pairs(const float* __restrict__ sb, int* __restrict__ gb, int cx, int cy, int rows2, const CoordPairs& c,
-                                              const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], f2 Fs, f2 Fs_rgb) {
+                                              const f2 (&T)[kPairs], const GradPairs& G, f2 (&R)[kPairs], f2 Fs, f2 Fs_rgb,
+                                              uint64_t* g_empty_bar, uint32_t g_empty_parity) {
     constexpr int RP = AOFF ? 3 * BW : 4 * BW, AP = AOFF ? BW : 4 * BW, A0 = AOFF ? AOFF : 3 * BW;
     const f2 m1 = splat(-1.0f), one = splat(1.0f);
     const f2 magic = splat(kFloorMagic), nmagic = splat(-kFloorMagic);
@@ -212,6 +226,8 @@ __device__ __forceinline__ bool bwd_box_pairs(const float* __restrict__ sb, int*
         const f2 wT = mul2(a, T[P]);
         R[P] = fma2(a, d, R[P]);
         // ---- scatter (grid_sampler_2d_backward), fixed point: colour channels one-step, alpha two-step ----
+        // The gradient box is needed only from here on: the flushers get the first pair's sampling time to finish emptying it.
+        if (GMPI_BWD_LATE_WAIT && P == 0) mbar_wait(g_empty_bar, g_empty_parity);
         const f2 wF = mul2(wT, Fs_rgb);                 // exact (power of two)
         int* ga = gb + idx[2 * P];
         int* gq = gb + idx[2 * P + 1];
@@ -249,7 +265,7 @@ __device__ __forceinline__ void flush_box(int* __restrict__ gb, const GradMeta& 
 #pragma unroll
         for (int k = 0; k < kRowsPerWarp; ++k) {
             const int r = fw + k * kBwdFlushWarps;
-            a[k] = r < gm.rows ? *reinterpret_cast<const int4*>(gb + r * pitch + cell0) : make_int4(0, 0, 0, 0);
+            a[k] = *reinterpret_cast<const int4*>(gb + r * pitch + cell0);      // rows beyond gm.rows are never written: they read 0
         }
         const int tx = gm.bx0 + 4 * x4;
         const bool col_ok = (unsigned)tx < (unsigned)Wt;          // bx0 % 4 == 0 and Wt % 4 == 0: a quad is inside or outside as a whole
@@ -452,19 +468,22 @@ mpi_bwd_box_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, c
                     const float* tr = sb + kBwdPlaneFloats + (kPairs * warp + P) * kTileW + lane;
                     T[P] = make_float2(tr[0], tr[32]);
                 }
-                // ---- gradient box of this (tile, plane): wait until the flushers have emptied it, then sample and scatter ----
-                mbar_wait(&g_empty[b], gph ^ 1u);
+                // ---- gradient box of this (tile, plane): sample, wait until the flushers have emptied it, scatter ----
+                if (!GMPI_BWD_LATE_WAIT) mbar_wait(&g_empty[b], gph ^ 1u);
                 int* gb = s_grad + b * kBwdPlaneFloats;
                 constexpr int AO = kFactored ? kBwdAlphaOff : 0;
                 bool done = false;
                 if (warp_fast) {   // warp-uniform, one-hot class
-                    if (sel & (1 << 18)) done = bwd_box_pairs<72, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
-                    else if (sel & (1 << 17)) done = bwd_box_pairs<64, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
-                    else if (sel & (1 << 19)) done = bwd_box_pairs<80, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
-                    else if (sel & (1 << 16)) done = bwd_box_pairs<56, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
-                    else if (sel & (1 << 20)) done = bwd_box_pairs<88, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb);
+                    if (sel & (1 << 18)) done = bwd_box_pairs<72, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb, &g_empty[b], gph ^ 1u);
+                    else if (sel & (1 << 17)) done = bwd_box_pairs<64, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb, &g_empty[b], gph ^ 1u);
+                    else if (sel & (1 << 19)) done = bwd_box_pairs<80, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb, &g_empty[b], gph ^ 1u);
+                    else if (sel & (1 << 16)) done = bwd_box_pairs<56, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb, &g_empty[b], gph ^ 1u);
+                    else if (sel & (1 << 20)) done = bwd_box_pairs<88, AO>(sb, gb, mt.cx, mt.cy, mt.rows2, cc, T, G, R, Fs, Fs_rgb, &g_empty[b], gph ^ 1u);
                 }
                 const int cls = done ? 0 : -1;
+                // a warp that did not use the box still waits: it must not arrive on g_full[b] a second time before the flushers
+                // have taken the previous fill (the arrival counts of two fills would mix)
+                if (GMPI_BWD_LATE_WAIT && !done) mbar_wait(&g_empty[b], gph ^ 1u);
                 __syncwarp();
                 mbar_arrive_if(&s_empty[s], lane_ == 0);    // taps and transmittance are consumed: hand the stage back
                 if (warp == 0 && lane == 0) {               // (warp 0 always has a row inside the image)

@@ -43,6 +43,14 @@ constexpr int kMaxPlanesStaged = GMPI_MAX_PLANES_STAGED;   // plane-constant tab
 constexpr int kCtasPerSm = GMPI_CTAS_PER_SM;
 constexpr int kStageFloats = kMaxBW * kMaxBH * 4;
 constexpr size_t kStagedSmem = (size_t)kStages * kStageFloats * 4 + (size_t)kMaxPlanesStaged * 32;
+// Factored forward: box widths 64 and 96 only.  Its boxes are [row][3][bw] (colour) and [row][bw] (alpha): row pitches of 3 bw and
+// bw words, and only a pitch that is a multiple of the 32 banks keeps a warp whose 32 taps straddle two texture rows (any rotated
+// view) at one wavefront per LDS -- the expanded box [row][4][bw] has that for every bw % 8 == 0.  Measured with 56..88-wide
+// boxes (profiles/r02_fwdfact_ncu.txt): 121 M bank-conflict wavefronts per launch against 57 M expanded, kernel 16 % slower.
+constexpr int kWideBW = 96;
+constexpr int kWideStageFloats = kWideBW * kMaxBH * 4;
+constexpr size_t kStagedSmemWide = (size_t)kStages * kWideStageFloats * 4 + (size_t)kMaxPlanesStaged * 32;
+static_assert(kStagedSmemWide + 1024 <= 227 * 1024, "wide factored ring must fit one SM");
 
 struct TmaMaps {
     CUtensorMap m[kNumMaps];      // expanded rgba [M*N][4][Ht][Wt] as (x, channel, y, plane), box {bw, 4, 4 rows, 1}
@@ -310,9 +318,19 @@ struct FwdRing {
 #define GMPI_FWD_SLEEP 0      // measured: sleeping between polls costs the forward 1 % (the 3-stage ring wants its producer prompt)
 #endif
     static constexpr bool kSleepPolls = GMPI_FWD_SLEEP != 0;   // producer sleeps between polls of a full ring (see mbar_wait_sleep)
+    static constexpr bool kWideFact = false;
 };
-// factored MPI: the colour box [row][3][bw] starts the stage, the alpha box [row][bw] follows at this offset (floats)
-constexpr int kFwdAlphaOff = 3 * kMaxBW * kMaxBH;
+#ifndef GMPI_FWD_WIDE_FACT
+#define GMPI_FWD_WIDE_FACT 1
+#endif
+struct FwdRingWide {      // the factored forward's ring: 64- or 96-wide boxes (see kWideBW)
+    static constexpr int kTileRows = kTileH, kRingStages = kStages, kBoxMaxH = kMaxBH;
+    static constexpr int kPlaneFloats = kWideStageFloats, kStride = kWideStageFloats;
+    static constexpr bool kReverse = false;
+    static constexpr bool kSleepPolls = GMPI_FWD_SLEEP != 0;
+    static constexpr bool kWideFact = true;
+};
+// factored MPI: the colour box [row][3][bw] starts the stage, the alpha box [row][bw] follows after 3/4 of the stage
 
 // kFact: factored MPI (compile time: a run-time test of p.alpha in this loop cost the forward 1 %, the producer's per-stage latency
 // being on the critical path of a three-stage ring).
@@ -363,10 +381,13 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             const int bx0 = ((xmin - 1) >> 2) << 2, by0 = ymin - 1;
             const int need_w = xmax - bx0 + 3, need_h = ymax - ymin + 4;      // +1 east/south tap, +-1 slack
             int mode = 0;
-            if (!all_finite || need_w > kMaxBW || ((need_h + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp > kMaxBH) mode = 2;   // would not fit a ring stage
+            constexpr bool kWide = kFact && Ring::kWideFact;
+            constexpr int kBoxMaxW = kWide ? kWideBW : kMaxBW;
+            if (!all_finite || need_w > kBoxMaxW || ((need_h + kRowsPerOp - 1) / kRowsPerOp) * kRowsPerOp > kMaxBH) mode = 2;   // would not fit a ring stage
             else if (bx0 > Wt - 1 || bx0 + need_w - 1 < 0 || by0 > Ht - 1 || by0 + need_h - 1 < 0) mode = 1;
-            const int k = mode == 0 ? max(0, (need_w - kMinBW + kBWStep - 1) / kBWStep) : 0;
-            const int bw = kMinBW + k * kBWStep;
+            // width class k (tensor-map slot, one-hot bit 16 + k of the header); wide rings: slot 1 = 64, slot 4 = kWideBW
+            const int k = mode != 0 ? 0 : kWide ? (need_w <= 64 ? 1 : 4) : max(0, (need_w - kMinBW + kBWStep - 1) / kBWStep);
+            const int bw = (kWide && k == 4) ? kWideBW : kMinBW + k * kBWStep;
             const int n_ops = mode == 0 ? (need_h + kRowsPerOp - 1) / kRowsPerOp : 0;
             const int rows = n_ops * kRowsPerOp;
             if (Ring::kSleepPolls) mbar_wait_sleep(&s_empty[s], ph ^ 1);
@@ -449,12 +470,18 @@ __device__ __forceinline__ void store_tile_pixels(const RenderParams& p, int v, 
     store_pixel(p, v, img, (size_t)py * p.W + px, o[0], o[1], o[2], o[3]);
 }
 
+template <bool kFactored>
+using FwdRingFor = typename std::conditional<kFactored && GMPI_FWD_WIDE_FACT != 0, FwdRingWide, FwdRing>::type;
+
 template <bool kAlignCorners, bool kEmitT, bool kFactored>
 __global__ void __launch_bounds__(kStagedThreads, kCtasPerSm)
 mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps, const int tiles_x, const int tiles_y) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_buf = reinterpret_cast<float*>(smem_raw);   // the ring starts the dynamic segment (1024-byte aligned)
-    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kStageFloats * 4);   // [N] of the current view
+    using Ring = FwdRingFor<kFactored>;
+    constexpr int kRingFloats = Ring::kPlaneFloats;         // floats per ring stage
+    constexpr int kAOff = kFactored ? 3 * (kRingFloats / 4) : 0;      // factored: alpha box behind the colour box
+    PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(smem_raw + (size_t)kStages * kRingFloats * 4);   // [N] of the current view
     __shared__ StageMeta s_meta[kStages];
     __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
     __shared__ TileWalk s_walk;
@@ -482,7 +509,7 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const size_t img = (size_t)p.H * p.W;
 
     if (warp == kConsWarps) {
-        staged_producer<kAlignCorners, FwdRing, kFactored>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
+        staged_producer<kAlignCorners, Ring, kFactored>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
     } else {
         // ================================ consumer warps ================================
         // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them
@@ -560,15 +587,20 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
                 }
                 mbar_wait(&s_full[s], ph);
                 const StageMeta mt = s_meta[s];
-                const float* sb = s_buf + s * kStageFloats;
+                const float* sb = s_buf + s * kRingFloats;
                 const int sel = mt.sel;                  // warp-uniform; the producer already folded mode and plane range in
                 bool done = false;
-                if (warp_fast) {                         // most frequent classes first (FFHQ poses: 72 > 64 > 80 >> 56, 88)
-                    if (sel & (1 << 18)) done = sample_pairs<72, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 17)) done = sample_pairs<64, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 19)) done = sample_pairs<80, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 16)) done = sample_pairs<56, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
-                    else if (sel & (1 << 20)) done = sample_pairs<88, kFactored ? kFwdAlphaOff : 0>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                if (warp_fast) {
+                    if (Ring::kWideFact) {               // factored: two widths, both with bank-aligned row pitches
+                        if (sel & (1 << 20)) done = sample_pairs<kWideBW, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                        else if (sel & (1 << 17)) done = sample_pairs<64, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    } else {                             // most frequent classes first (FFHQ poses: 72 > 64 > 80 >> 56, 88)
+                        if (sel & (1 << 18)) done = sample_pairs<72, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                        else if (sel & (1 << 17)) done = sample_pairs<64, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                        else if (sel & (1 << 19)) done = sample_pairs<80, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                        else if (sel & (1 << 16)) done = sample_pairs<56, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                        else if (sel & (1 << 20)) done = sample_pairs<88, kAOff>(sb, mt.cx, mt.cy, mt.rows2, cc, T, cr, cg, cb, cws);
+                    }
                 }
                 if (!done) {
                     // ---- generic body: per-pixel range / box checks, direct sampling when not staged ----

@@ -374,9 +374,10 @@ static bool mpi_aligned(const RenderParams& p) {
 }
 
 // Tensor maps of the MPI (expanded or factored) for the five box-width classes.  Returns 0 on success.
-static int encode_mpi_maps(TmaMaps& maps, const RenderParams& p) {
+// wide: the factored forward's ring (FwdRingWide) -- slot 4 holds the kWideBW-wide boxes, slot 1 the 64-wide ones, the rest unused.
+static int encode_mpi_maps(TmaMaps& maps, const RenderParams& p, bool wide = false) {
     for (int k = 0; k < kNumMaps; ++k) {
-        const int bw = kMinBW + k * kBWStep;
+        const int bw = (wide && k == kNumMaps - 1) ? kWideBW : kMinBW + k * kBWStep;
         if (p.alpha) {
             if (encode_color_map(&maps.rgb[k], p.rgb, (uint64_t)p.M, p.Ht, p.Wt, bw, kRowsPerOp) != 0) return -1;
             if (p.bg_rgb && encode_color_map(&maps.bg[k], p.bg_rgb, (uint64_t)p.M, p.Ht, p.Wt, bw, kRowsPerOp) != 0) return -1;
@@ -398,9 +399,10 @@ static int device_sms(int* sms) {
 template <bool AC, bool EMIT, bool FAC>
 static cudaError_t launch_fwd_staged(const RenderParams& p, const TmaMaps& maps, int grid, int tiles_x, int tiles_y, cudaStream_t st) {
     auto kernel = mpi_fwd_staged_kernel<AC, EMIT, FAC>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem);
+    constexpr size_t smem = FwdRingFor<FAC>::kWideFact ? kStagedSmemWide : kStagedSmem;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kStagedThreads, kStagedSmem, st>>>(p, maps, tiles_x, tiles_y);
+    kernel<<<grid, kStagedThreads, smem, st>>>(p, maps, tiles_x, tiles_y);
     return cudaSuccess;
 }
 
@@ -426,7 +428,7 @@ static int launch_fwd(RenderParams p, cudaStream_t st) {
     const bool ac = (p.options & GMPI_ALIGN_CORNERS) != 0, emit = p.transmittance != nullptr, fac = p.alpha != nullptr;
     if (staged_eligible(p.V, p.N, p.Ht, p.Wt, p.H, p.W) && mpi_aligned(p) && (size_t)p.M * p.N < ((size_t)1 << 31)) {
         TmaMaps maps;
-        if (encode_mpi_maps(maps, p) != 0) {
+        if (encode_mpi_maps(maps, p, fac && FwdRingFor<true>::kWideFact) != 0) {
             if (g_fwd_variant.load(std::memory_order_relaxed) == 2) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         } else {
             int sms = 0;

@@ -26,6 +26,11 @@ print('$v', 'fwd', round(d['value'], 1), 'fps', round(d['roofline']['frac'], 4),
     multi)  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > $OUT/${TAG}_pytest_multi.log 2>&1; echo "multi pytest rc=$?"; tail -4 $OUT/${TAG}_pytest_multi.log ;;
     benchn) NG=$(nvidia-smi -L | wc -l); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG --steps 20 --warmup 5 > $OUT/${TAG}_bench_n$NG.json 2> $OUT/${TAG}_bench_n$NG.err; echo "bench n=$NG rc=$?"; tail -c 800 $OUT/${TAG}_bench_n$NG.err; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus $NG --steps 2 --warmup 1 --ref-budget-s 40 > $OUT/${TAG}_ref_n$NG.json 2> $OUT/${TAG}_ref_n$NG.err; echo "ref n=$NG rc=$?" ;;
     ncuextra) for w in fwdfact c4 c4flat; do timeout 400 ncu --set full --clock-control none -k regex:mpi_fwd_staged -c 1 -o $OUT/${TAG}_prof_$w python tools/run_one.py $w > $OUT/${TAG}_ncu_$w.log 2>&1; echo "ncu $w rc=$?"; done ;;
+    abtrain) for rep in 1 2; do for v in $ABV; do GMPI_LIB_PATH=$PWD/ml_gmpi_b200/libgmpi_mpi_render_$v.so timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-reference-on-gpu 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$v', 'fwd', round(d['roofline']['kernel_ms'], 4), 'ms; train', round(d['train_step']['ms_per_step'], 3), 'ms', round(d['train_step']['roofline_frac'], 4), 'C5', round(d['configs']['C5_train_512']['ms_per_step'], 3), 'N1', round(d['configs']['N1_factored_fwd']['ms_per_step'], 4))" | tee -a $OUT/${TAG}_abtrain.txt; done; done ;;
+    vtests) for v in ${VTV:-$ABV}; do GMPI_LIB_PATH=$PWD/ml_gmpi_b200/libgmpi_mpi_render_$v.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_features.py -m gpu -x -q -k "backward or grad or non_projective or factored or bwd" > $OUT/${TAG}_pytest_$v.log 2>&1; echo "$v pytest rc=$?"; tail -3 $OUT/${TAG}_pytest_$v.log; done ;;
     *) echo "unknown step $step" ;;
   esac
 done
