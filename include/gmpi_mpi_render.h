@@ -57,7 +57,7 @@ extern "C" {
 #define GMPI_ALIGN_CORNERS 1u          /* MPI(align_corners=True), configs/gmpi.yml:74          */
 #define GMPI_CHECK_LAST_PLANE 2u       /* assert_not_out_of_last_plane, mpi.py:317              */
 #define GMPI_COLOR_MINUS1_1 4u         /* fuse "2*color-1" of mpi_renderer.py:467 into the store */
-#define GMPI_ZERO_GRAD 8u              /* bwd: zero g_rgba on the stream before accumulating    */
+#define GMPI_ZERO_GRAD 8u              /* bwd: zero the gradient buffers on the stream before accumulating */
 #define GMPI_U8_ROUND_HALF_UP 16u       /* uint8 epilogue: clamp, x*255+0.5 (torchvision save_image, fid_evaluation.py:125-130)
                                           instead of numpy's truncating astype (render_video.py:119-126) */
 
@@ -209,8 +209,8 @@ typedef struct gmpi_render_desc {
     void* stream;
 } gmpi_render_desc;
 
-/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: lets a caller zero the gradient buffers on a SIDE stream while the training forward
- * runs (the memset is a copy-engine operation, the forward kernel owns every SM), instead of GMPI_ZERO_GRAD's in-line memset. */
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`, for callers that accumulate into their own buffers (no GMPI_ZERO_GRAD).  Note that a
+ * memset cannot overlap the staged kernels, on whatever stream (they own every SM: measured, tools/zero_overlap_probe.py). */
 int gmpi_mpi_zero_async(void* ptr, size_t bytes, void* stream);
 
 int gmpi_mpi_render_fwd_ex(const gmpi_render_desc* desc);
@@ -277,6 +277,10 @@ int gmpi_debug_plane_coords_packed(const int32_t* view2mpi, const float* dhw, co
 
 /* Test hook: force the forward kernel variant: 0 auto (default), 1 direct-gather, 2 TMA-staged. */
 int gmpi_debug_set_fwd_variant(int variant);
+
+/* GMPI_ZERO_GRAD of the staged backward as stream memsets before the kernel (0, default) or inside the kernel, one MPI slab
+ * ahead of use (1: correct for any view order, measured 4.5 % slower on B200 -- see mpi_bwd_box.cuh). */
+int gmpi_debug_set_bwd_zero(int in_kernel);
 
 /* Test hook (host only): tile order for a tile height (30 forward, 24 backward) and view grouping (gmpi_render_desc.view_group). */
 int gmpi_debug_tile_walk_ex(int H, int W, int V, int tile_h, int view_group, int grid, int cta, int* out_v_px0_py0, int max_tiles);

@@ -334,9 +334,14 @@ struct FwdRingWide {      // the factored forward's ring: 64- or 96-wide boxes (
 
 // kFact: factored MPI (compile time: a run-time test of p.alpha in this loop cost the forward 1 %, the producer's per-stage latency
 // being on the critical path of a three-stage ring).
-template <bool kAlignCorners, class Ring, bool kFact>
+struct NoPacer { static constexpr bool kActive = false; };      // the forward's producer has no side job
+
+// Pacer: an optional side job of the producer warp (the backward's gradient zeroing): before_tile(mpi) ahead of a tile's first
+// copy; new_stage() then chunk() between the polls of the wait for a free ring stage (chunk() returns false when there is nothing
+// to do); at_end() after the last tile.
+template <bool kAlignCorners, class Ring, bool kFact, class Pacer>
 __device__ __forceinline__ void staged_producer(const RenderParams& p, const TmaMaps& maps, float* s_buf, StageMeta* s_meta,
-                                            uint64_t* s_full, uint64_t* s_empty, const TileWalk* s_walk, int lane) {
+                                            uint64_t* s_full, uint64_t* s_empty, const TileWalk* s_walk, int lane, Pacer& pacer) {
     constexpr bool kReverse = Ring::kReverse;
     constexpr int kStride = Ring::kStride;      // floats per ring stage
     constexpr int kTileH = Ring::kTileRows, kStages = Ring::kRingStages, kMaxBH = Ring::kBoxMaxH, kStageFloats = Ring::kPlaneFloats;
@@ -355,6 +360,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
     for (int j = 0; s_walk->at(j, txy); ++j) {
         const int v = txy.v, px0 = txy.px0, py0 = txy.py0;
         const int m = __ldg(p.view2mpi + v);
+        if constexpr (Pacer::kActive) pacer.before_tile(m);
         float ev[3], zd[3];
         load_eye_z(p, v, ev, zd);
         // the four corner pixels of the tile (replicated over the warp), clamped into the image
@@ -390,8 +396,15 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             const int bw = (kWide && k == 4) ? kWideBW : kMinBW + k * kBWStep;
             const int n_ops = mode == 0 ? (need_h + kRowsPerOp - 1) / kRowsPerOp : 0;
             const int rows = n_ops * kRowsPerOp;
-            if (Ring::kSleepPolls) mbar_wait_sleep(&s_empty[s], ph ^ 1);
-            else mbar_wait(&s_empty[s], ph ^ 1);
+            if constexpr (Pacer::kActive) {      // the side job fills the wait for a free stage, a few stores between polls
+                pacer.new_stage();
+                while (!mbar_try_wait(&s_empty[s], ph ^ 1))
+                    if (!pacer.chunk()) __nanosleep(96);
+            } else if (Ring::kSleepPolls) {
+                mbar_wait_sleep(&s_empty[s], ph ^ 1);
+            } else {
+                mbar_wait(&s_empty[s], ph ^ 1);
+            }
             if (lane == 0) {
                 StageMeta mt;
                 mt.cx = kFloorMagicBits + bx0; mt.cy = kFloorMagicBits + by0;
@@ -418,6 +431,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
             }
         }
     }
+    if constexpr (Pacer::kActive) pacer.at_end();
 }
 
 // 4x4 transpose inside every quad of lanes (4 q .. 4 q + 3): on entry lane k of a quad holds a[c] = M[k][c], on return
@@ -509,7 +523,8 @@ mpi_fwd_staged_kernel(const RenderParams p, const __grid_constant__ TmaMaps maps
     const size_t img = (size_t)p.H * p.W;
 
     if (warp == kConsWarps) {
-        staged_producer<kAlignCorners, Ring, kFactored>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane);
+        NoPacer np;
+        staged_producer<kAlignCorners, Ring, kFactored>(p, maps, s_buf, s_meta, s_full, s_empty, &s_walk, lane, np);
     } else {
         // ================================ consumer warps ================================
         // warp w owns rows kPairs*w .. kPairs*w + kPairs-1 of the tile; a lane owns x = lane and lane+32 on each of them

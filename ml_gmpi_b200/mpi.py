@@ -25,16 +25,6 @@ def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-_side_streams = {}
-
-
-def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=key)
-    return _side_streams[key]
-
-
 def _as_f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -68,20 +58,6 @@ class _RenderFn(torch.autograd.Function):
             _lib.check(lib.gmpi_mpi_render_fwd_ex(ctypes.byref(d)))
         ctx.save_for_backward(rgba, rgb, alpha, bg_rgb, dhw, view2mpi, ray_dir, eye, z_dir, trans)
         ctx.options, ctx.view_group = options, view_group
-        ctx.grad_bufs = None
-        if trans is not None:
-            # Gradient buffers are allocated NOW and zeroed on a side stream: the memset (a copy-engine operation, 16 B per
-            # texel-plane) overlaps the forward kernel instead of preceding the backward kernel on the critical path.
-            bufs = [torch.empty_like(t) if t is not None else None for t in (rgba, rgb, alpha, bg_rgb)]
-            side = _side_stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))        # the allocator may hand out blocks still in use upstream
-            with torch.cuda.device(dev):
-                for b in bufs:
-                    if b is not None:
-                        _lib.check(lib.gmpi_mpi_zero_async(b.data_ptr(), b.numel() * 4, side.cuda_stream))
-            ev = torch.cuda.Event()
-            ev.record(side)
-            ctx.grad_bufs = (bufs, ev)
         ctx.set_materialize_grads(False)
         return color, depth
 
@@ -103,13 +79,9 @@ class _RenderFn(torch.autograd.Function):
             g_color = torch.zeros((V, 3, H, W), device=dev, dtype=torch.float32)
         g_color = _as_f32c(g_color)
         g_depth = _as_f32c(g_depth) if g_depth is not None else None
-        zero_opt = _lib.OPT_ZERO_GRAD
-        if ctx.grad_bufs is not None:      # zeroed during the forward (first backward through this node only)
-            (g_rgba, g_rgb, g_alpha, g_bg), ev = ctx.grad_bufs
-            ctx.grad_bufs = None
-            torch.cuda.current_stream(dev).wait_event(ev)
-            zero_opt = 0
-        elif factored:
+        # GMPI_ZERO_GRAD: the callee zeroes the buffers on the stream.  (Zeroing them on a side stream during the forward, as an
+        # earlier version did, buys nothing: a memset cannot overlap the persistent kernels -- tools/zero_overlap_probe.py.)
+        if factored:
             g_rgba = None
             g_rgb, g_alpha = torch.empty_like(rgb), torch.empty_like(alpha)
             g_bg = torch.empty_like(bg_rgb) if bg_rgb is not None else None
@@ -117,7 +89,7 @@ class _RenderFn(torch.autograd.Function):
             g_rgb = g_alpha = g_bg = None
             g_rgba = torch.empty_like(rgba)
         with torch.cuda.device(dev):   # autograd worker threads do not inherit the device
-            d = _lib.make_desc(options=ctx.options | zero_opt, M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W,
+            d = _lib.make_desc(options=ctx.options | _lib.OPT_ZERO_GRAD, M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W,
                                view_group=ctx.view_group, rgba=rgba, rgb=rgb, alpha=alpha, bg_rgb=bg_rgb, view2mpi=view2mpi, dhw=dhw,
                                ray_dir=ray_dir, eye=eye, z_dir=z_dir, transmittance=trans, g_color=g_color, g_depth=g_depth,
                                g_rgba=g_rgba, g_rgb=g_rgb, g_bg_rgb=g_bg, g_alpha=g_alpha, stream=_stream_ptr(dev))

@@ -468,8 +468,8 @@ def test_plan_query_names_the_direct_kernel_cliffs():
 
 
 def test_backward_twice_and_interleaved_graphs_use_fresh_gradient_buffers():
-    """The gradient buffers are allocated and zeroed (side stream) during the forward; a second backward through the same node
-    (retain_graph) and two graphs alive at once must not share or re-use them."""
+    """Every backward allocates its own gradient buffers (zeroed by the backward kernel itself): a second backward through the same
+    node (retain_graph) and two graphs alive at once must not share or re-use them."""
     from ml_gmpi_b200 import synth
     d = dev()
     case = synth.make_case(n_planes=16, tex=256, img=256, n_mpi=2, views_per_mpi=2, seed=31, device=d, last_alpha_one=True)
@@ -487,3 +487,83 @@ def test_backward_twice_and_interleaved_graphs_use_fresh_gradient_buffers():
     n = lambda t: t.cpu().numpy()
     assert rel_err(n(g1b), n(g1)) <= 1e-6 and rel_err(n(g2), 2 * n(g1)) <= 1e-6
     assert float(g1.abs().max()) > 0
+
+
+def _bwd_c_abi(case, trans, gc, gdp, g_rgba, options):
+    """gmpi_mpi_render_bwd_ex straight through the C ABI into a caller-owned gradient buffer."""
+    import ctypes
+    from ml_gmpi_b200 import _lib
+    lib = _lib.load()
+    M, N, _, Ht, Wt = case.rgba.shape
+    V, _, H, W = case.ray_dir.shape
+    d = _lib.make_desc(options=options, M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W, rgba=case.rgba, view2mpi=case.view2mpi, dhw=case.dhw,
+                       ray_dir=case.ray_dir, eye=case.eye, z_dir=case.z_dir, transmittance=trans, g_color=gc, g_depth=gdp,
+                       g_rgba=g_rgba, stream=torch.cuda.current_stream(case.rgba.device).cuda_stream)
+    _lib.check(lib.gmpi_mpi_render_bwd_ex(ctypes.byref(d)))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("order", ["sorted", "interleaved", "reversed"])
+def test_zero_grad_inside_the_backward_kernel_poisoned_buffer_any_view_order(order):
+    """GMPI_ZERO_GRAD on the staged backward, as stream memsets (default) and with the kernel zeroing the gradient itself, one MPI
+    slab ahead of the tiles that add to it (GradZeroPacer, gmpi_debug_set_bwd_zero(1)).  The buffer arrives full of NaN; views of three MPIs come sorted by MPI (MPI.forward's layout), interleaved
+    or reversed (the protocol must be correct -- and must not deadlock -- for any order); the result must equal the oracle and the
+    memset mode."""
+    import ctypes
+    from ml_gmpi_b200 import synth, _lib
+    lib = _lib.load()
+    d = dev()
+    case = synth.make_case(n_planes=12, tex=256, img=256, n_mpi=3, views_per_mpi=2, seed=77, device=d, last_alpha_one=True)
+    perm = {"sorted": [0, 1, 2, 3, 4, 5], "interleaved": [0, 2, 4, 1, 3, 5], "reversed": [5, 4, 3, 2, 1, 0]}[order]
+    pi = torch.tensor(perm, device=d)
+    import dataclasses
+    case = dataclasses.replace(case, view2mpi=case.view2mpi[pi].contiguous(), ray_dir=case.ray_dir[pi].contiguous(),
+                               eye=case.eye[pi].contiguous(), z_dir=case.z_dir[pi].contiguous())
+    M, N, _, Ht, Wt = case.rgba.shape
+    V, _, H, W = case.ray_dir.shape
+    opt = _lib.OPT_ALIGN_CORNERS
+    color, depth = torch.empty((V, 3, H, W), device=d), torch.empty((V, 1, H, W), device=d)
+    trans = torch.empty((V, N, H, W), device=d)
+    flags = torch.zeros(1, dtype=torch.int32, device=d)
+    fd = _lib.make_desc(options=opt, M=M, V=V, N=N, Ht=Ht, Wt=Wt, H=H, W=W, rgba=case.rgba, view2mpi=case.view2mpi, dhw=case.dhw,
+                        ray_dir=case.ray_dir, eye=case.eye, z_dir=case.z_dir, color=color, depth=depth, transmittance=trans, flags=flags,
+                        stream=torch.cuda.current_stream(d).cuda_stream)
+    _lib.check(lib.gmpi_mpi_render_fwd_ex(ctypes.byref(fd)))
+    gen = torch.Generator().manual_seed(9)
+    gc = torch.randn(color.shape, generator=gen).to(d)
+    gdp = torch.randn(depth.shape, generator=gen).to(d)
+    n = lambda t: t.detach().cpu().numpy()
+    ref = mpi_oracle.backward(n(case.rgba), n(case.view2mpi), n(case.dhw), n(case.ray_dir), n(case.eye), n(case.z_dir), n(gc), n(gdp))
+    out = {}
+    try:
+        for mode in (1, 0):
+            lib.gmpi_debug_set_bwd_zero(mode)
+            gbuf = torch.full_like(case.rgba, float("nan"))
+            _bwd_c_abi(case, trans, gc, gdp, gbuf, opt | _lib.OPT_ZERO_GRAD)
+            assert bool(torch.isfinite(gbuf).all()), f"mode {mode}: poison survived"
+            out[mode] = n(gbuf)
+            assert rel_err(out[mode], ref) <= 2e-5
+    finally:
+        lib.gmpi_debug_set_bwd_zero(0)
+    assert rel_err(out[1], out[0]) <= 1e-6
+    # without GMPI_ZERO_GRAD the kernel accumulates into what it is given
+    gacc = torch.ones_like(case.rgba)
+    _bwd_c_abi(case, trans, gc, gdp, gacc, opt)
+    assert rel_err(n(gacc) - 1.0, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("in_kernel", [0, 1])
+def test_zero_grad_one_mpi_many_views_poisoned_allocator_block(in_kernel):
+    """One MPI with many views (in-kernel mode: the whole zeroing precedes the first tile) through autograd: the gradient buffer
+    is a torch.empty block that held NaN a moment ago."""
+    from ml_gmpi_b200 import synth, _lib
+    d = dev()
+    case = synth.make_case(n_planes=16, tex=256, img=256, n_mpi=1, views_per_mpi=6, seed=5, device=d, last_alpha_one=True)
+    lib = _lib.load()
+    lib.gmpi_debug_set_bwd_zero(in_kernel)
+    try:
+        poison = torch.full_like(case.rgba, float("nan"))
+        del poison                                                  # the next same-size torch.empty gets this block back
+        assert _grad_check(case, with_depth=True) <= 2e-5
+    finally:
+        lib.gmpi_debug_set_bwd_zero(0)

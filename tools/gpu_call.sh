@@ -31,6 +31,8 @@ import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('$v', 'fwd', round(d['roofline']['kernel_ms'], 4), 'ms; train', round(d['train_step']['ms_per_step'], 3), 'ms', round(d['train_step']['roofline_frac'], 4), 'C5', round(d['configs']['C5_train_512']['ms_per_step'], 3), 'N1', round(d['configs']['N1_factored_fwd']['ms_per_step'], 4))" | tee -a $OUT/${TAG}_abtrain.txt; done; done ;;
     vtests) for v in ${VTV:-$ABV}; do GMPI_LIB_PATH=$PWD/ml_gmpi_b200/libgmpi_mpi_render_$v.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_features.py -m gpu -x -q -k "backward or grad or non_projective or factored or bwd" > $OUT/${TAG}_pytest_$v.log 2>&1; echo "$v pytest rc=$?"; tail -3 $OUT/${TAG}_pytest_$v.log; done ;;
+    zprobe) timeout 300 python tools/zero_overlap_probe.py > $OUT/${TAG}_zprobe.txt 2>&1; echo "zprobe rc=$?"; tail -2 $OUT/${TAG}_zprobe.txt ;;
+    zab) for v in $ABV; do for fr in $FRACS; do GMPI_LIB_PATH=$PWD/ml_gmpi_b200/libgmpi_mpi_render_$v.so GMPI_ZERO_FRAC=$fr timeout 200 python tools/zero_ab.py 2>&1 | tail -1 | tee -a $OUT/${TAG}_zab.txt; done; done ;;
     *) echo "unknown step $step" ;;
   esac
 done
