@@ -734,6 +734,23 @@ def leg_configs(job, args):
                               "roofline_frac_of_factored_bytes": alg_f / (ms * 1e-3) / 1e9 / peak,
                               "bytes_vs_expanded": alg_f / (algorithmic_bytes_fwd(NP, R, R, R, R) * B)}
     assert int(flags.item()) == 0
+    if be.name == "cuda":       # the factored TRAIN step: gradients per factor (g_rgb [B,3,T,T] summed over planes, g_alpha [B,N,1,T,T])
+        torch = be.torch
+        rgb_g, alpha_g = rgb.requires_grad_(True), alpha.requires_grad_(True)
+        gcol = torch.randn((B, 3, R, R), device=be.device)
+
+        def fb_factored():
+            rgb_g.grad = alpha_g.grad = None
+            c, _ = be.g.render_views_factored(rgb_g, alpha_g, case.dhw, case.view2mpi, case.ray_dir, case.eye, case.z_dir,
+                                              color_minus1_1=True)
+            (c * gcol).sum().backward()
+        ms_t = job.timed(fb_factored, max(3, steps // 4), warmup=2)
+        assert alpha_g.grad is not None and bool(torch.isfinite(alpha_g.grad.flatten()[:1024]).all())
+        out["N1_factored_train"] = {"workload": f"{NP} planes, {R}^2, batch {B} per GPU, forward + backward from / to the factors",
+                                    "value": world * B / (ms_t * 1e-3), "unit": "frames/s (forward+backward)", "ms_per_step": ms_t}
+        rgb_g.requires_grad_(False); alpha_g.requires_grad_(False)
+        rgb_g.grad = alpha_g.grad = None
+        del gcol
     # N3: LightRenderer.compute_depth on the same alpha stack (light_renderer.py:82-100): one streaming pass, 4 B per texel-plane
     if be.name == "cuda":
         from ml_gmpi_b200.light import alpha_depth

@@ -63,6 +63,11 @@ struct BwdRing {
 #endif
     static constexpr bool kSleepPolls = GMPI_BWD_SLEEP != 0;
     static constexpr bool kWideFact = false;     // the backward keeps the 56..88-wide classes: its shared memory is full
+    static constexpr bool kBinaryCopies = false; // expanded MPI: one 4-row copy per lane (see staged_producer)
+    // factored MPI: colour box = 3 copies of 12 rows (row offset r * 3 * bw * 4 bytes must be a multiple of 128 for bw = 56..88,
+    // i.e. r a multiple of 4; 18-row halves gave cudaErrorMisalignedAddress)
+    static constexpr int kColourCopyRows = 12;
+    static_assert(kBwdMaxBH % kColourCopyRows == 0 && kColourCopyRows % 4 == 0, "colour copies tile the box, 128-byte aligned");
 };
 
 struct GradPairs {

@@ -54,8 +54,10 @@ static_assert(kStagedSmemWide + 1024 <= 227 * 1024, "wide factored ring must fit
 
 struct TmaMaps {
     CUtensorMap m[kNumMaps];      // expanded rgba [M*N][4][Ht][Wt] as (x, channel, y, plane), box {bw, 4, 4 rows, 1}
-    // factored MPI: shared colour [M][3][Ht][Wt] as (x, channel, y, mpi), box {bw, 3, 4 rows, 1}; the last plane's own colour
-    // (torgba_sep_background) likewise; per-plane alpha [M*N][Ht][Wt] as (x, y, plane), box {bw, 4 rows, 1}
+    CUtensorMap m8[kNumMaps], m16[kNumMaps], m32[kNumMaps];   // the same with 8-, 16- and 32-row boxes (see staged_producer: a
+                                                              // footprint of r 4-row chunks goes out as the binary digits of r)
+    // factored MPI: shared colour [M][3][Ht][Wt] as (x, channel, y, mpi), box {bw, 3, the ring's kColourCopyRows, 1}; the last
+    // plane's own colour (torgba_sep_background) likewise; per-plane alpha [M*N][Ht][Wt] as (x, y, plane), box {bw, box height, 1}
     CUtensorMap rgb[kNumMaps], bg[kNumMaps], a[kNumMaps];
     CUtensorMap t;      // backward only: saved transmittance [V*N][H][W], box {64, 24, 1} (the backward's tile)
 };
@@ -319,16 +321,23 @@ struct FwdRing {
 #endif
     static constexpr bool kSleepPolls = GMPI_FWD_SLEEP != 0;   // producer sleeps between polls of a full ring (see mbar_wait_sleep)
     static constexpr bool kWideFact = false;
+    static constexpr bool kBinaryCopies = true;            // expanded MPI: copies of 32/16/8/4 rows (see staged_producer)
+    static constexpr int kColourCopyRows = kMaxBH;         // factored MPI (only with GMPI_FWD_WIDE_FACT=0): one colour copy
 };
 #ifndef GMPI_FWD_WIDE_FACT
 #define GMPI_FWD_WIDE_FACT 1
 #endif
+static_assert(kMaxBH % 2 == 0 && kMaxBH / kRowsPerOp < 16, "half-height colour copies; binary digits of the chunk count");
 struct FwdRingWide {      // the factored forward's ring: 64- or 96-wide boxes (see kWideBW)
     static constexpr int kTileRows = kTileH, kRingStages = kStages, kBoxMaxH = kMaxBH;
     static constexpr int kPlaneFloats = kWideStageFloats, kStride = kWideStageFloats;
     static constexpr bool kReverse = false;
     static constexpr bool kSleepPolls = GMPI_FWD_SLEEP != 0;
     static constexpr bool kWideFact = true;
+    static constexpr bool kBinaryCopies = true;
+    // factored MPI: colour box = 2 copies of 22 rows.  A copy lands at row offset r * 3 * bw * 4 bytes, which must be a multiple
+    // of 128 (TMA destination alignment): any r for bw = 64 / 96.
+    static constexpr int kColourCopyRows = kMaxBH / 2;
 };
 // factored MPI: the colour box [row][3][bw] starts the stage, the alpha box [row][bw] follows after 3/4 of the stage
 
@@ -352,7 +361,7 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
     const size_t img = (size_t)p.H * p.W;
     if (lane < kNumMaps) {
         if (kFact) { tma_prefetch_desc(&maps.rgb[lane]); tma_prefetch_desc(&maps.a[lane]); }
-        else tma_prefetch_desc(&maps.m[lane]);
+        else { tma_prefetch_desc(&maps.m[lane]); tma_prefetch_desc(&maps.m8[lane]); tma_prefetch_desc(&maps.m16[lane]); tma_prefetch_desc(&maps.m32[lane]); }
     }
     int p_stage = 0;
     uint32_t p_phase = 0;
@@ -411,22 +420,41 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
                 mt.rows2 = rows - 2;
                 mt.sel = bw | (mode << 8) | ((mode == 0 && pc.fast != 0.0f ? (1 << k) : kSelSlow) << 16);
                 s_meta[s] = mt;
-                if (n_ops > 0 || kTBytes) mbar_arrive_expect_tx(&s_full[s], (uint32_t)(rows * bw * 16) + kTBytes);
+                // bytes the copies of this stage will deliver (a box counts whole, zero-filled parts included)
+                const uint32_t tx = (uint32_t)((kFact ? kMaxBH : rows) * bw * 16);
+                if (n_ops > 0 || kTBytes) mbar_arrive_expect_tx(&s_full[s], (n_ops > 0 ? tx : 0u) + kTBytes);
                 else mbar_arrive(&s_full[s]);
                 if (kReverse)   // the tile's saved transmittance for this plane rides in the same stage
                     tma_load_3d(s_buf + (size_t)s * kStride + kStageFloats, &maps.t, &s_full[s], px0, py0, v * N + i);
             }
             __syncwarp();
-            if (lane < n_ops) {
-                if (kFact) {         // factored MPI: shared colour (or the last plane's own) + this plane's alpha, two boxes
-                    float* stage = s_buf + (size_t)s * kStride;
+            // Few, tall copies.  UTMALDG takes uniform operands, so the lanes of a warp issue their copies ONE AFTER ANOTHER: with a
+            // 4-row copy per lane (9-11 per stage, twice that for the factored MPI) the producer was the bottleneck of its own ring
+            // (profiles/README.md, round 2: factored forward 1.61 -> 1.41 ms with three copies per stage).
+            if (n_ops > 0) {
+                float* stage = s_buf + (size_t)s * kStride;
+                if (kFact) {
+                    // factored MPI: the colour box (shared image, or the last plane's own) as two or three copies that tile the
+                    // ring's box height, the alpha box as one copy of the full height.  Rows beyond the footprint are fetched and never
+                    // read: the colour image is shared by all planes and comes from L2, alpha is a quarter of the bytes.
+                    constexpr int kCR = Ring::kColourCopyRows;      // (a copy's destination must be 128-byte aligned, see the rings)
+                    static_assert(kMaxBH % kCR == 0, "colour copies tile the box");
                     const CUtensorMap* cmap = (p.bg_rgb && i == N - 1) ? &maps.bg[k] : &maps.rgb[k];
-                    tma_load_4d(stage + (size_t)lane * kRowsPerOp * 3 * bw, cmap, &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m);
-                    tma_load_3d(stage + (kStageFloats / 4) * 3 + (size_t)lane * kRowsPerOp * bw, &maps.a[k], &s_full[s], bx0,
-                                by0 + lane * kRowsPerOp, m * N + i);
-                } else {
-                    float* dst = s_buf + (size_t)s * kStride + (size_t)lane * kRowsPerOp * 4 * bw;
-                    tma_load_4d(dst, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
+                    if (lane < kMaxBH / kCR) tma_load_4d(stage + (size_t)lane * kCR * 3 * bw, cmap, &s_full[s], bx0, 0, by0 + lane * kCR, m);
+                    if (lane == 31) tma_load_3d(stage + (kStageFloats / 4) * 3, &maps.a[k], &s_full[s], bx0, by0, m * N + i);
+                } else if (!Ring::kBinaryCopies) {
+                    // expanded MPI, backward: one 4-row copy per lane (measured: taller copies make its 2-stage ring 0.5 % slower)
+                    if (lane < n_ops)
+                        tma_load_4d(stage + (size_t)lane * kRowsPerOp * 4 * bw, &maps.m[k], &s_full[s], bx0, 0, by0 + lane * kRowsPerOp, m * N + i);
+                } else if (lane < 4) {
+                    // expanded MPI, forward (HBM-bound: no over-fetch): the n_ops 4-row chunks go out as the binary digits of n_ops,
+                    // one copy of 32, 16, 8 and 4 rows each where the digit is set -- at most three copies for up to 44 rows (-1.1 %)
+                    const int bit = 3 - lane;
+                    if ((n_ops >> bit) & 1) {
+                        const int before = (n_ops >> (bit + 1)) << (bit + 1);      // chunks covered by the taller copies
+                        const CUtensorMap* mp = bit == 3 ? &maps.m32[k] : bit == 2 ? &maps.m16[k] : bit == 1 ? &maps.m8[k] : &maps.m[k];
+                        tma_load_4d(stage + (size_t)before * kRowsPerOp * 4 * bw, mp, &s_full[s], bx0, 0, by0 + before * kRowsPerOp, m * N + i);
+                    }
                 }
             }
         }

@@ -374,16 +374,19 @@ static bool mpi_aligned(const RenderParams& p) {
 }
 
 // Tensor maps of the MPI (expanded or factored) for the five box-width classes.  Returns 0 on success.
+// box_h, colour_rows: the ring's box height and kColourCopyRows (factored: colour copies of colour_rows rows, one alpha copy of box_h).
 // wide: the factored forward's ring (FwdRingWide) -- slot 4 holds the kWideBW-wide boxes, slot 1 the 64-wide ones, the rest unused.
-static int encode_mpi_maps(TmaMaps& maps, const RenderParams& p, bool wide = false) {
+static int encode_mpi_maps(TmaMaps& maps, const RenderParams& p, int box_h, int colour_rows, bool wide = false) {
     for (int k = 0; k < kNumMaps; ++k) {
         const int bw = (wide && k == kNumMaps - 1) ? kWideBW : kMinBW + k * kBWStep;
         if (p.alpha) {
-            if (encode_color_map(&maps.rgb[k], p.rgb, (uint64_t)p.M, p.Ht, p.Wt, bw, kRowsPerOp) != 0) return -1;
-            if (p.bg_rgb && encode_color_map(&maps.bg[k], p.bg_rgb, (uint64_t)p.M, p.Ht, p.Wt, bw, kRowsPerOp) != 0) return -1;
-            if (encode_slab_map(&maps.a[k], p.alpha, (uint64_t)p.M * p.N, p.Ht, p.Wt, bw, kRowsPerOp, 1) != 0) return -1;
-        } else if (encode_plane_map(&maps.m[k], p.rgba, (uint64_t)p.M * p.N, p.Ht, p.Wt, bw, kRowsPerOp) != 0) {
-            return -1;
+            if (encode_color_map(&maps.rgb[k], p.rgb, (uint64_t)p.M, p.Ht, p.Wt, bw, colour_rows) != 0) return -1;
+            if (p.bg_rgb && encode_color_map(&maps.bg[k], p.bg_rgb, (uint64_t)p.M, p.Ht, p.Wt, bw, colour_rows) != 0) return -1;
+            if (encode_slab_map(&maps.a[k], p.alpha, (uint64_t)p.M * p.N, p.Ht, p.Wt, bw, box_h, 1) != 0) return -1;
+        } else {
+            CUtensorMap* const by_rows[4] = {&maps.m[k], &maps.m8[k], &maps.m16[k], &maps.m32[k]};
+            for (int b = 0; b < 4; ++b)
+                if (encode_plane_map(by_rows[b], p.rgba, (uint64_t)p.M * p.N, p.Ht, p.Wt, bw, kRowsPerOp << b) != 0) return -1;
         }
     }
     return 0;
@@ -428,7 +431,7 @@ static int launch_fwd(RenderParams p, cudaStream_t st) {
     const bool ac = (p.options & GMPI_ALIGN_CORNERS) != 0, emit = p.transmittance != nullptr, fac = p.alpha != nullptr;
     if (staged_eligible(p.V, p.N, p.Ht, p.Wt, p.H, p.W) && mpi_aligned(p) && (size_t)p.M * p.N < ((size_t)1 << 31)) {
         TmaMaps maps;
-        if (encode_mpi_maps(maps, p, fac && FwdRingFor<true>::kWideFact) != 0) {
+        if (encode_mpi_maps(maps, p, kMaxBH, FwdRingFor<true>::kColourCopyRows, fac && FwdRingFor<true>::kWideFact) != 0) {
             if (g_fwd_variant.load(std::memory_order_relaxed) == 2) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         } else {
             int sms = 0;
@@ -541,7 +544,7 @@ static int launch_bwd(RenderParams p, cudaStream_t st) {
     p.eye0 = p.eye;
     if (p.view_group < 1) p.view_group = 1;
     TmaMaps maps;
-    if (encode_mpi_maps(maps, p) != 0) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (encode_mpi_maps(maps, p, kBwdMaxBH, BwdRing::kColourCopyRows) != 0) return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     if (encode_slab_map(&maps.t, p.transmittance, (uint64_t)p.V * p.N, p.H, p.W, kTileW, kBwdTileH, 1) != 0)
         return fail(GMPI_ERR_CUDA, "cuTensorMapEncodeTiled (transmittance) failed");
     int sms = 0;
