@@ -17,10 +17,6 @@ for step in "$@"; do
     ncubwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:mpi_bwd -c 1 -o $OUT/${TAG}_prof_bwd python tools/run_one.py bwd > $OUT/${TAG}_ncu_bwd.log 2>&1; echo "ncu bwd rc=$?" ;;
     ncufwd) timeout 600 ncu --set full --clock-control none --import-source on -k regex:mpi_fwd_staged -c 1 -o $OUT/${TAG}_prof_fwd python tools/run_one.py fwd > $OUT/${TAG}_ncu_fwd.log 2>&1; echo "ncu fwd rc=$?" ;;
     sanitize) timeout 900 compute-sanitizer --tool racecheck python tools/run_one.py small > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 $OUT/${TAG}_racecheck.log; timeout 900 compute-sanitizer --tool memcheck python tools/run_one.py small > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 $OUT/${TAG}_memcheck.log ;;
-    ab)     for v in sleep nosleep; do GMPI_LIB_PATH=$PWD/ml_gmpi_b200/libgmpi_mpi_render_$v.so timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-configs --no-reference-on-gpu 2>/dev/null | python -c "
-import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$v', 'fwd', round(d['value'], 1), 'fps', round(d['roofline']['frac'], 4), round(d['roofline']['kernel_ms'], 4), 'ms; train', round(d['train_step']['ms_per_step'], 3), 'ms', round(d['train_step']['roofline_frac'], 4))" | tee -a $OUT/${TAG}_ab.txt; done ;;
     fwdab)  timeout 300 python tools/fwd_ab.py r02a - minimal scalarepi 2>&1 | tee $OUT/${TAG}_fwdab.txt ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-configs --no-reference-on-gpu > $OUT/${TAG}_launches_bench.log 2>&1; echo "launches rc=$?" ;;
     multi)  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > $OUT/${TAG}_pytest_multi.log 2>&1; echo "multi pytest rc=$?"; tail -4 $OUT/${TAG}_pytest_multi.log ;;
