@@ -561,10 +561,14 @@ static int launch_bwd(RenderParams p, cudaStream_t st) {
         const size_t tex = (size_t)p.Ht * p.Wt;
         if (g_bwd_zero_in_kernel.load(std::memory_order_relaxed) &&
             cudaMallocAsync(reinterpret_cast<void**>(&zero_flags), sizeof(unsigned) * (size_t)p.M, st) == cudaSuccess) {
-            GMPI_CUDA_OK(cudaMemsetAsync(zero_flags, 0, sizeof(unsigned) * (size_t)p.M, st));
-            if (fac) {
-                GMPI_CUDA_OK(cudaMemsetAsync(p.g_rgb, 0, sizeof(float) * (size_t)p.M * 3 * tex, st));
-                if (p.g_bg_rgb) GMPI_CUDA_OK(cudaMemsetAsync(p.g_bg_rgb, 0, sizeof(float) * (size_t)p.M * 3 * tex, st));
+            cudaError_t ez = cudaMemsetAsync(zero_flags, 0, sizeof(unsigned) * (size_t)p.M, st);
+            if (ez == cudaSuccess && fac) {
+                ez = cudaMemsetAsync(p.g_rgb, 0, sizeof(float) * (size_t)p.M * 3 * tex, st);
+                if (ez == cudaSuccess && p.g_bg_rgb) ez = cudaMemsetAsync(p.g_bg_rgb, 0, sizeof(float) * (size_t)p.M * 3 * tex, st);
+            }
+            if (ez != cudaSuccess) {
+                (void)cudaFreeAsync(zero_flags, st);
+                GMPI_CUDA_OK(ez);
             }
             p.zero_base = reinterpret_cast<float4*>(fac ? p.g_alpha : p.g_rgba);
             p.zero_slab16 = (unsigned long long)p.N * (fac ? 1 : 4) * tex / 4;            // Wt % 4 == 0: whole float4s
