@@ -282,6 +282,10 @@ int gmpi_debug_set_fwd_variant(int variant);
  * ahead of use (1: correct for any view order, measured 4.5 % slower on B200 -- see mpi_bwd_box.cuh). */
 int gmpi_debug_set_bwd_zero(int in_kernel);
 
+/* Test hook (host only): the TMA copies the expanded forward issues for a footprint of n_rows staged rows, as (first row, rows)
+ * pairs: the binary digits of n_rows / 4 (copies of 32, 16, 8, 4 rows).  Returns the number of copies. */
+int gmpi_debug_copy_plan(int n_rows, int* out_row_rows, int max_copies);
+
 /* Test hook (host only): tile order for a tile height (30 forward, 24 backward) and view grouping (gmpi_render_desc.view_group). */
 int gmpi_debug_tile_walk_ex(int H, int W, int V, int tile_h, int view_group, int grid, int cta, int* out_v_px0_py0, int max_tiles);
 

@@ -25,7 +25,7 @@ ABI_VERSION = 2
 
 EXPORTS = [
     "gmpi_abi_version", "gmpi_last_error", "gmpi_mpi_render_fwd_variant", "gmpi_mpi_render_fwd",
-    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_set_bwd_zero", "gmpi_debug_plane_coords_packed", "gmpi_debug_tile_walk",
+    "gmpi_mpi_render_fwd_gather", "gmpi_mpi_render_fwd_train", "gmpi_mpi_render_bwd", "gmpi_mpi_render_bwd_saved", "gmpi_mpi_check_range", "gmpi_mpi_render_fwd_host", "gmpi_mpi_release_host_cache", "gmpi_debug_plane_coords", "gmpi_debug_division", "gmpi_debug_set_fwd_variant", "gmpi_debug_set_bwd_zero", "gmpi_debug_copy_plan", "gmpi_debug_plane_coords_packed", "gmpi_debug_tile_walk",
     "gmpi_mpi_render_fwd_plan", "gmpi_mpi_render_fwd_ex", "gmpi_mpi_render_bwd_ex", "gmpi_mpi_render_host_ex",
     "gmpi_debug_tile_walk_ex", "gmpi_debug_cam_rays",
     "gmpi_mpi_zero_async", "gmpi_mpi_alpha_depth_fwd", "gmpi_mpi_alpha_depth_bwd", "gmpi_mpi_apply_shading_fwd", "gmpi_mpi_apply_shading_bwd",
@@ -111,6 +111,8 @@ def load():
     lib.gmpi_debug_set_fwd_variant.argtypes = [i]
     lib.gmpi_debug_set_bwd_zero.restype = i
     lib.gmpi_debug_set_bwd_zero.argtypes = [i]
+    lib.gmpi_debug_copy_plan.restype = i
+    lib.gmpi_debug_copy_plan.argtypes = [i, vp, i]
     lib.gmpi_debug_tile_walk.restype = i
     lib.gmpi_debug_tile_walk.argtypes = [i, i, i, i, i, vp, i]
     lib.gmpi_debug_tile_walk_ex.restype = i

@@ -343,6 +343,15 @@ struct FwdRingWide {      // the factored forward's ring: 64- or 96-wide boxes (
 
 // kFact: factored MPI (compile time: a run-time test of p.alpha in this loop cost the forward 1 %, the producer's per-stage latency
 // being on the critical path of a three-stage ring).
+// The expanded forward's copies of one stage: the footprint's n_chunks 4-row chunks as the binary digits of n_chunks.  Lane 0..3
+// owns the digit 8, 4, 2, 1: returns the copy's height in chunks (0: this lane issues nothing) and, in `before`, the chunks
+// covered by the taller copies, i.e. where this copy starts.  (Host-evaluable: gmpi_debug_copy_plan, tests/test_tile_walk.py.)
+__host__ __device__ __forceinline__ int binary_copy_of_lane(int n_chunks, int lane, int& before) {
+    const int bit = 3 - lane;
+    before = (n_chunks >> (bit + 1)) << (bit + 1);
+    return ((n_chunks >> bit) & 1) << bit;
+}
+
 struct NoPacer { static constexpr bool kActive = false; };      // the forward's producer has no side job
 
 // Pacer: an optional side job of the producer warp (the backward's gradient zeroing): before_tile(mpi) ahead of a tile's first
@@ -449,10 +458,10 @@ __device__ __forceinline__ void staged_producer(const RenderParams& p, const Tma
                 } else if (lane < 4) {
                     // expanded MPI, forward (HBM-bound: no over-fetch): the n_ops 4-row chunks go out as the binary digits of n_ops,
                     // one copy of 32, 16, 8 and 4 rows each where the digit is set -- at most three copies for up to 44 rows (-1.1 %)
-                    const int bit = 3 - lane;
-                    if ((n_ops >> bit) & 1) {
-                        const int before = (n_ops >> (bit + 1)) << (bit + 1);      // chunks covered by the taller copies
-                        const CUtensorMap* mp = bit == 3 ? &maps.m32[k] : bit == 2 ? &maps.m16[k] : bit == 1 ? &maps.m8[k] : &maps.m[k];
+                    int before;
+                    const int h = binary_copy_of_lane(n_ops, lane, before);
+                    if (h) {
+                        const CUtensorMap* mp = h == 8 ? &maps.m32[k] : h == 4 ? &maps.m16[k] : h == 2 ? &maps.m8[k] : &maps.m[k];
                         tma_load_4d(stage + (size_t)before * kRowsPerOp * 4 * bw, mp, &s_full[s], bx0, 0, by0 + before * kRowsPerOp, m * N + i);
                     }
                 }

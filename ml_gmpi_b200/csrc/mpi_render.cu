@@ -656,6 +656,22 @@ int gmpi_debug_tile_walk_ex(int H, int W, int V, int tile_h, int view_group, int
     return n;
 }
 
+// Host evaluation of the expanded forward's copies of one stage (same code as the producer): for a footprint of n_rows staged rows
+// (a multiple of 4, at most the ring's box height) writes (first row, rows) of every copy; returns their number.
+int gmpi_debug_copy_plan(int n_rows, int* out_row_rows, int max_copies) {
+    if (n_rows < 0 || n_rows % kRowsPerOp != 0 || n_rows > kMaxBH || max_copies < 0 || (max_copies > 0 && !out_row_rows))
+        return -fail(GMPI_ERR_INVALID_ARGUMENT, "gmpi_debug_copy_plan: n_rows must be a multiple of %d in [0, %d]", kRowsPerOp, kMaxBH);
+    int n = 0;
+    for (int lane = 0; lane < 4; ++lane) {
+        int before;
+        const int h = binary_copy_of_lane(n_rows / kRowsPerOp, lane, before);
+        if (!h) continue;
+        if (n < max_copies) { out_row_rows[2 * n] = before * kRowsPerOp; out_row_rows[2 * n + 1] = h * kRowsPerOp; }
+        ++n;
+    }
+    return n;
+}
+
 int gmpi_debug_tile_walk(int H, int W, int V, int grid, int cta, int* out_v_px0_py0, int max_tiles) {
     return gmpi_debug_tile_walk_ex(H, W, V, kTileH, 1, grid, cta, out_v_px0_py0, max_tiles);
 }

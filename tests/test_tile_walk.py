@@ -89,3 +89,25 @@ def test_grouped_walk_covers_every_tile_once(H, W, V, tile_h, group, grid):
 
 def test_group_that_does_not_divide_v_falls_back_to_view_major():
     assert walk_ex(256, 256, 7, 30, 4, 148, 0) == walk_ex(256, 256, 7, 30, 1, 148, 0)
+
+
+@pytest.mark.parametrize("n_rows", list(range(0, 48, 4)))
+def test_copy_plan_tiles_the_footprint_with_at_most_three_copies(n_rows):
+    """The expanded forward stages a footprint of n_rows rows as the binary digits of n_rows / 4 (TMA copies of 32, 16, 8, 4 rows;
+    UTMALDG copies are issued one after another, so few tall ones): they must tile [0, n_rows) exactly, tallest first."""
+    lib = _lib.load()
+    out = np.zeros((4, 2), dtype=np.int32)
+    n = lib.gmpi_debug_copy_plan(n_rows, out.ctypes.data_as(ctypes.c_void_p), 4)
+    copies = [tuple(int(x) for x in r) for r in out[:n]]
+    assert n == bin(n_rows // 4).count("1") <= 3
+    row = 0
+    for first, rows in copies:
+        assert first == row and rows in (32, 16, 8, 4)
+        row += rows
+    assert row == n_rows
+    assert [r for _, r in copies] == sorted((r for _, r in copies), reverse=True)
+
+
+def test_copy_plan_rejects_bad_row_counts():
+    lib = _lib.load()
+    assert lib.gmpi_debug_copy_plan(6, None, 0) < 0 and lib.gmpi_debug_copy_plan(48, None, 0) < 0 and lib.gmpi_debug_copy_plan(-4, None, 0) < 0
