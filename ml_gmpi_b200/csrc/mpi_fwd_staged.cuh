@@ -2,8 +2,8 @@
 //
 // One CTA per SM walks (tile, plane) pairs: a 64x30-pixel output tile, planes front to back.  A producer warp computes,
 // from the tile's four corner rays, the texel footprint of the tile on the next plane and issues cp.async.bulk.tensor
-// copies of exactly that footprint (all four channels, 4-row chunks, origin aligned to 16 bytes, width rounded up to one
-// of five compile-time classes) into a 3-stage shared-memory ring; 15 consumer warps (4 pixels = 2 packed f32x2 pairs per
+// copies of exactly that footprint (all four channels, rows in units of 4 issued as a few tall copies, origin aligned to 16 bytes,
+// width rounded up to one of five compile-time classes) into a 3-stage shared-memory ring; 15 consumer warps (4 pixels = 2 packed f32x2 pairs per
 // thread) take their 16 bilinear taps per pixel and plane from shared memory (a warp reads 32 consecutive x of one row:
 // conflict-free while the texel/pixel scale is <= 1) and composite in registers.  TMA's out-of-bounds zero fill implements
 // padding_mode="zeros".  Every consumer warp verifies (one vote) that all its taps lie inside the staged box; otherwise it
