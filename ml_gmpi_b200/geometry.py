@@ -63,3 +63,64 @@ FFHQ = dict(  # curriculums.py:109-116, configs/gmpi.yml:74-96
     sphere_center=(0.0, 0.0, 1.0), sphere_r=1.0, h_mean=0.0, h_std=0.289, v_mean=0.0, v_std=0.127, n_truncated_stds=2,
     confined=True,
 )
+
+
+# ---- texel positions of the planes: what the generator is conditioned on and what LightRenderer shades with --------------------
+# Mirrors MPIRenderer.comput_tex_pixels_3d_coords / comput_tex_pixels_3d_normalized_coords_mpi / get_xyz_single_res(only_z) /
+# get_xyz_interpolate_ws (gmpi/core/mpi_renderer.py:182-318).  Callers: train.py:328,467,818, fid_evaluation.py:90,
+# eval/vis/render_video.py:193-205, eval/prepare_fake_data.py:141-153 -- `mpi_tex_pix_xyz` is also LightRenderer.render's third
+# argument (train.py:540,708).  World frame: +X right, +Y down, +Z forward; texel (row r, col c) of plane i sits at
+# (lin_w[c]*w_i/2, lin_h[r]*h_i/2, d_i), border texels ON the plane's edge (= align_corners=True sampling).
+
+def texel_xyzd(dhw: torch.Tensor, tex_h: int, tex_w: int) -> torch.Tensor:
+    """dhw [N,3] (distance, metric height, metric width) -> [N,tex_h,tex_w,4] = (x, y, z, |xyz|), same dtype/device as dhw.
+    (mpi_renderer.py:252-291; the 4th channel is the distance to the world origin, computed before any transformation.)"""
+    n = dhw.shape[0]
+    half_w = dhw[:, 2:3] / 2.0                                                      # [N,1]
+    half_h = dhw[:, 1:2] / 2.0
+    x = (torch.linspace(-1, 1, tex_w, device=dhw.device) * half_w).view(n, 1, tex_w)
+    y = (torch.linspace(-1, 1, tex_h, device=dhw.device) * half_h).view(n, tex_h, 1)
+    out = torch.empty((n, tex_h, tex_w, 4), dtype=dhw.dtype, device=dhw.device)
+    out[..., 0] = x
+    out[..., 1] = y
+    out[..., 2] = dhw[:, 0].view(n, 1, 1)
+    out[..., 3] = torch.linalg.vector_norm(out[..., :3], ord=2, dim=3)
+    return out
+
+
+def normalize_xyz(xyz: torch.Tensor, last_plane_hw, plane_min_d: float, plane_max_d: float, xyz_range: str = "-11") -> torch.Tensor:
+    """[...,3] world positions -> the MPI volume's unit box: x by the LAST (largest) plane's width, y by its height, z by
+    [plane_min_d, plane_max_d]; "01" -> [0,1], "-11" -> [-1,1] (mpi_renderer.py:293-318)."""
+    assert xyz_range in ("01", "-11"), xyz_range
+    h, w = float(last_plane_hw[0]), float(last_plane_hw[1])
+    lo = torch.tensor([-np.float32(w) / 2, -np.float32(h) / 2, plane_min_d], dtype=torch.float32, device=xyz.device)
+    hi = torch.tensor([np.float32(w) / 2, np.float32(h) / 2, plane_max_d], dtype=torch.float32, device=xyz.device)
+    u = (xyz[..., :3] - lo) / (hi - lo)
+    return 2 * u - 1 if xyz_range == "-11" else u
+
+
+def plane_z(dhw: torch.Tensor, plane_min_d: float, plane_max_d: float, xyz_range: str = "-11"):
+    """only_z conditioning: (z [N,1,1,1], z normalised by the depth range) (mpi_renderer.py:183-196)."""
+    assert xyz_range in ("01", "-11"), xyz_range
+    z = dhw[:, 0].reshape(-1, 1, 1, 1)
+    u = (z - plane_min_d) / (plane_max_d - plane_min_d)
+    return z, (2 * u - 1 if xyz_range == "-11" else u)
+
+
+def plane_interpolation_weights(plane_min_d: float, plane_max_d: float, n_src: int, n_tgt: int, method: str = "inverse") -> torch.Tensor:
+    """[n_tgt, n_src+2] fp32: row t holds the two linear-interpolation weights of target plane t between its neighbouring
+    source planes; columns 0 and n_src+1 are placeholder planes at -/+999999 (mpi_renderer.py:209-250; used to render an MPI
+    generated with n_src planes at n_tgt planes, eval/vis/render_video.py:193, eval/prepare_fake_data.py:141).  One
+    searchsorted instead of the reference's n_tgt x n_src Python loop."""
+    src = torch.empty(n_src + 2, dtype=torch.float32)
+    src[0], src[-1] = -999999, 999999
+    src[1:-1] = torch.from_numpy(sample_distance(plane_min_d, plane_max_d, n_src, method))
+    tgt = torch.from_numpy(sample_distance(plane_min_d, plane_max_d, n_tgt, method))
+    j = torch.searchsorted(src, tgt, right=True) - 1                               # src[j] <= tgt < src[j+1]
+    lo, hi = src[j], src[j + 1]
+    den = (hi - lo) + 1e-8
+    ws = torch.zeros((n_tgt, n_src + 2), dtype=torch.float32)
+    rows = torch.arange(n_tgt)
+    ws[rows, j] = (hi - tgt) / den
+    ws[rows, j + 1] = (tgt - lo) / den
+    return ws

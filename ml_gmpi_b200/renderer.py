@@ -9,7 +9,10 @@ Differences, all on the fast side:
   * `2*color-1` (`:467`) is fused into the render kernel's store;
   * rays for all views are generated in one batched matmul instead of a Python loop (`:370-376`);
   * the 10 001-pose envelope of the constructor is vectorised (7.7 s -> ~10 ms).
-The generator-side helpers `get_xyz*` (`:154-318`) are not part of the render path and stay in the reference.
+The generator-side helpers `get_xyz*` (`:154-318`: texel positions the generator is conditioned on and LightRenderer shades
+with) are mirrored too, so the whole façade can be swapped, not only `MPI`: same return values, but the per-resolution tables
+are built once and cached (the reference rebuilds 4^2 ... tex^2 on every `get_xyz(ret_single_res=False)`, i.e. every training
+iteration, train.py:467,818), and the "disparity" option returns new tensors instead of inverting the cache in place.
 """
 import logging
 from typing import Optional
@@ -19,7 +22,7 @@ import torch
 
 from . import _lib
 from .camera import PinholeCamera, focal_from_fov, sample_yaw_pitch, sphere_poses
-from .geometry import plane_dhw_table
+from .geometry import normalize_xyz, plane_dhw_table, plane_interpolation_weights, plane_z, texel_xyzd
 from .mpi import MPI, check_range, render_views
 
 logger = logging.getLogger("ml_gmpi_b200")
@@ -71,6 +74,65 @@ class MPIRenderer:
         self.static_mpi_plane_dhws = torch.from_numpy(table)
         self.dynamic_mpi_plane_dhws = self.static_mpi_plane_dhws
         self._dhw_dev = None
+        self._xyz_cache = {}
+        self.mpi_tex_h = self.mpi_tex_w = None
+
+    # mpi_renderer.py:154-180
+    def get_xyz(self, tex_h, tex_w, ret_single_res=True, only_z=False):
+        assert tex_h == tex_w, f"Only support square resolution now. Receiving {tex_h} x {tex_w}."
+        assert tex_h >= 4 and tex_h & (tex_w - 1) == 0, f"{tex_h}"                # a power of two
+        if ret_single_res:
+            return self.get_xyz_single_res(tex_h, tex_w, only_z=only_z)
+        if self.use_xyz_ztype not in ("depth", "disparity"):
+            raise ValueError(self.use_xyz_ztype)
+        xyz_dict, normalized_xyz_dict = {}, {}
+        res = 4
+        while res <= tex_h:                                                        # 4, 8, ..., tex_h
+            xyz, nxyz = self.get_xyz_single_res(res, res, only_z=only_z)
+            if self.use_xyz_ztype == "disparity":                                  # mpi_renderer.py:175-176
+                xyz = xyz.clone()
+                xyz[..., 2] = 1 / xyz[..., 2]
+            xyz_dict[res], normalized_xyz_dict[res] = xyz, nxyz
+            res *= 2
+        return xyz_dict, normalized_xyz_dict
+
+    # mpi_renderer.py:182-207
+    def get_xyz_single_res(self, tex_h, tex_w, only_z=False):
+        if only_z:
+            z, nz = plane_z(self.dynamic_mpi_plane_dhws, self.plane_min_d, self.plane_max_d, self.normalized_xyz_range)
+            return z.to(self.device), nz.to(self.device)
+        self.comput_tex_pixels_3d_coords(tex_h, tex_w)
+        return self.mpi_tex_pix_3d_coords[..., :3], (self.mpi_tex_pix_3d_normalized_coords if self.use_normalized_xyz else None)
+
+    # mpi_renderer.py:209-250
+    def get_xyz_interpolate_ws(self, n_src_planes, n_tgt_planes):
+        return plane_interpolation_weights(self.plane_min_d, self.plane_max_d, n_src_planes, n_tgt_planes,
+                                           self.plane_distances_sample_method)
+
+    # mpi_renderer.py:252-291 (+ :293-318): [#planes, tex_h, tex_w, 4] = (x, y, z, distance to the origin), cached per size
+    def comput_tex_pixels_3d_coords(self, tex_h, tex_w):
+        key = (int(tex_h), int(tex_w))
+        hit = self._xyz_cache.get(key)
+        if hit is None or hit[0] is not self.dynamic_mpi_plane_dhws:
+            xyzd = texel_xyzd(self.dynamic_mpi_plane_dhws, tex_h, tex_w).to(self.device)
+            hit = (self.dynamic_mpi_plane_dhws, xyzd, self._normalized(xyzd))
+            self._xyz_cache[key] = hit
+        self.mpi_tex_h, self.mpi_tex_w = tex_h, tex_w
+        self.mpi_tex_pix_3d_coords, self.mpi_tex_pix_3d_normalized_coords = hit[1], hit[2]
+        self.non_jittered_xyz = hit[1][..., :3]
+
+    def _normalized(self, raw_xyz):
+        return normalize_xyz(raw_xyz, self.static_mpi_plane_dhws[-1, 1:3], self.plane_min_d, self.plane_max_d, self.normalized_xyz_range)
+
+    # mpi_renderer.py:293-318
+    def comput_tex_pixels_3d_normalized_coords_mpi(self, raw_xyz):
+        self.mpi_tex_pix_3d_normalized_coords = self._normalized(raw_xyz)
+
+    # mpi_renderer.py:320-335
+    def view_info_from_c2w_mat(self, camera, c2w, device=torch.device("cpu")):
+        tf_c2w = c2w if isinstance(c2w, torch.Tensor) else torch.as_tensor(np.asarray(c2w), dtype=torch.float32)
+        ray_dir, eye, z_dir = camera.generate_rays(tf_c2w.view(1, 4, 4))
+        return ray_dir.float(), eye.view(1, 3).float(), z_dir.view(1, 3).float(), tf_c2w.unsqueeze(0)
 
     # mpi_renderer.py:337-385 (batched)
     def sample_cam_poses(self, batch_size, horizontal_mean, horizontal_std, vertical_mean, vertical_std, random_pose,
