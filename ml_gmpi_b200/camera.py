@@ -58,6 +58,87 @@ class PinholeCamera:
         return rays.contiguous(), c2w[:, :3, 3].contiguous(), rot[:, :, 2].contiguous()
 
 
+class Camera:
+    """The reference's general-intrinsics camera, same constructor / properties / `generate_rays` contract
+    (gmpi/core/camera.py:13-211): K is any 3x3 upper-triangular intrinsic matrix (focal lengths, skew, principal point),
+    `generate_rays(tf_c2w [4,4] numpy or torch, border_only)` -> (ray_dir [3,H,W] (or [3,2,2] for the image corners), eye [3],
+    z_dir [3]), numpy in -> fp64 numpy out, torch in -> fp32 torch out.  K^-1 [u v 1] is evaluated in closed form (back
+    substitution) instead of `np.linalg.inv` + matmul; the render path itself uses the batched `PinholeCamera`."""
+
+    def __init__(self, height: int = 480, width: int = 640, intrinsics: np.ndarray = None, ray_from_pix_center: bool = False):
+        assert intrinsics is not None and intrinsics.ndim == 2 and intrinsics.shape[0] == 3 and intrinsics.shape[1] == 3, (
+            "[Camera] Expecting a 3x3 intrinsics matrix, but instead got {}".format(None if intrinsics is None else intrinsics.shape))
+        self._h, self._w, self._K = height, width, intrinsics
+        self._ray_from_pix_center = ray_from_pix_center
+        self._cache = {}
+
+    intrinsic_matrix = property(lambda self: self._K)
+    height = property(lambda self: self._h)
+    width = property(lambda self: self._w)
+
+    def __repr__(self):
+        return f"Camera: height={self.height}, width={self.width}, intrinsics=\n{self.intrinsic_matrix}"
+
+    def _unproject(self, u: np.ndarray, v: np.ndarray) -> np.ndarray:
+        """K^-1 [u v 1]^T by back substitution (K upper triangular): [3, ...] fp64."""
+        K = np.asarray(self._K, np.float64)
+        assert K[1, 0] == 0 and K[2, 0] == 0 and K[2, 1] == 0 and K[2, 2] != 0, "intrinsics must be upper triangular"
+        z = 1.0 / K[2, 2]
+        y = (v - K[1, 2] * z) / K[1, 1]
+        x = (u - K[0, 1] * y - K[0, 2] * z) / K[0, 0]
+        return np.stack(np.broadcast_arrays(x, y, np.full((1, 1), z)))
+
+    @property
+    def homogeneous_coordinates(self) -> np.ndarray:                    # [3,H,W], camera.py:53-76
+        if "hom" not in self._cache:
+            off = 0.5 if self._ray_from_pix_center else 0.0
+            self._cache["hom"] = self._unproject(np.arange(int(self.width), dtype=np.float64)[None, :] + off,
+                                                 np.arange(int(self.height), dtype=np.float64)[:, None] + off)
+        return self._cache["hom"]
+
+    @property
+    def homogeneous_coordinates_border(self) -> np.ndarray:             # [3,2,2]: the image corners, camera.py:78-96
+        if "homb" not in self._cache:
+            self._cache["homb"] = self._unproject(np.array([[0.0, self.width]]), np.array([[0.0], [self.height]]))
+        return self._cache["homb"]
+
+    @staticmethod
+    def _unit(d):
+        return (d / np.linalg.norm(d, axis=0)).reshape(3, -1)
+
+    ray_dir_np = property(lambda self: self._unit(self.homogeneous_coordinates))                   # [3,H*W] fp64, camera.py:98-105
+    ray_dir_border_np = property(lambda self: self._unit(self.homogeneous_coordinates_border))     # [3,4]
+
+    def _dirs_torch(self, device, border_only):
+        key = (str(device), bool(border_only))
+        if key not in self._cache:
+            d = self.ray_dir_border_np if border_only else self.ray_dir_np
+            self._cache[key] = torch.from_numpy(d).float().to(device)                              # camera.py:116-130
+        return self._cache[key]
+
+    ray_dir_torch = property(lambda self: self._dirs_torch("cpu", False))
+    ray_dir_border_torch = property(lambda self: self._dirs_torch("cpu", True))
+
+    def ray_dir_torch_cuda(self, device, border_only=False) -> torch.Tensor:
+        return self._dirs_torch(device, border_only)
+
+    def generate_rays(self, tf_c2w, border_only: bool = False):
+        shape = (3, 2, 2) if border_only else (3, self.height, self.width)
+        if isinstance(tf_c2w, np.ndarray):                                                         # camera.py:154-180
+            rot = tf_c2w[:3, :3]
+            return (rot @ (self.ray_dir_border_np if border_only else self.ray_dir_np)).reshape(shape), tf_c2w[:3, 3], rot[:, 2]
+        if isinstance(tf_c2w, torch.Tensor):                                                       # camera.py:182-211
+            rot = tf_c2w[:3, :3]
+            return torch.matmul(rot, self._dirs_torch(tf_c2w.device, border_only)).reshape(shape), tf_c2w[:3, 3], rot[:, 2]
+        raise ValueError
+
+
+def gen_cam(*, h, w, f, ray_from_pix_center):
+    """cam_utils.py:16-22: pinhole with the principal point at (w/2, h/2)."""
+    return Camera(height=h, width=w, intrinsics=np.array([[f, 0.0, w / 2], [0.0, f, h / 2], [0.0, 0.0, 1.0]]),
+                  ray_from_pix_center=ray_from_pix_center)
+
+
 def cam_params(c2w: torch.Tensor, focal: float, height: int, width: int, ray_from_pix_center: bool = True) -> torch.Tensor:
     """[V,16] fp32 = {f0, f1, f2, pixel-centre offset, R row-major (9), eye (3)} per view: the `cam` input of the kernels' fast
     mode (rays generated in the kernel with PinholeCamera's arithmetic instead of uploading ray_dir [V,3,H,W]).  The focal

@@ -131,7 +131,11 @@ class MPIRenderer:
     # mpi_renderer.py:320-335
     def view_info_from_c2w_mat(self, camera, c2w, device=torch.device("cpu")):
         tf_c2w = c2w if isinstance(c2w, torch.Tensor) else torch.as_tensor(np.asarray(c2w), dtype=torch.float32)
-        ray_dir, eye, z_dir = camera.generate_rays(tf_c2w.view(1, 4, 4))
+        if isinstance(camera, PinholeCamera):                                      # batched [V,4,4] -> [V,3,H,W]
+            ray_dir, eye, z_dir = camera.generate_rays(tf_c2w.view(1, 4, 4))
+        else:                                                                      # the reference's contract: [4,4] -> [3,H,W]
+            ray_dir, eye, z_dir = camera.generate_rays(tf_c2w)
+            ray_dir = ray_dir.unsqueeze(0)
         return ray_dir.float(), eye.view(1, 3).float(), z_dir.view(1, 3).float(), tf_c2w.unsqueeze(0)
 
     # mpi_renderer.py:337-385 (batched)

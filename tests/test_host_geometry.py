@@ -70,3 +70,34 @@ def test_renderer_facade_constructor_matches_reference_table():
     np.testing.assert_allclose(torch.cat(infos[3]).numpy(), ref["ray_dir"], atol=3e-7)
     with pytest.raises(RuntimeError, match="CUDA devices only"):
         r.render(torch.rand(1, 8, 4, 16, 16), 20, 20)
+
+
+def test_general_camera_matches_reference_fixture_and_pinhole():
+    """`Camera` (the reference's general-K class, camera.py:13-211) against the reference fixture and against the batched
+    PinholeCamera the render path uses: same fp32 rays bit for bit."""
+    ref = load_golden("ffhq_cams_20")
+    f = camera.focal_from_fov(float(ref["fov"]), 20)
+    cam = camera.gen_cam(h=20, w=20, f=f, ray_from_pix_center=True)
+    pin = camera.PinholeCamera(20, 20, f)
+    assert cam.height == 20 and cam.width == 20 and cam.intrinsic_matrix[0, 2] == 10 and "Camera: height=20" in repr(cam)
+    assert torch.equal(cam.ray_dir_torch, pin.cam_dirs("cpu"))
+    np.testing.assert_allclose(cam.ray_dir_border_np, pin.border_dirs64(), atol=1e-15)
+    c2w = torch.from_numpy(ref["c2w"])
+    batched = pin.generate_rays(c2w)
+    for v in range(c2w.shape[0]):
+        ray, eye, z = cam.generate_rays(c2w[v])
+        assert ray.shape == (3, 20, 20) and torch.equal(eye, batched[1][v]) and torch.equal(z, batched[2][v])
+        np.testing.assert_allclose(ray.numpy(), ref["ray_dir"][v], atol=2e-7)
+        ray64, eye64, _ = cam.generate_rays(ref["c2w"][v].astype(np.float64))
+        assert ray64.dtype == np.float64 and np.abs(ray64 - ray.numpy()).max() < 2e-7
+    assert cam.generate_rays(ref["c2w"][0], border_only=True)[0].shape == (3, 2, 2)
+    with pytest.raises(ValueError):
+        cam.generate_rays([[1.0]])
+    with pytest.raises(AssertionError, match="Expecting a 3x3 intrinsics"):
+        camera.Camera(4, 4, np.eye(4))
+    # skew and an off-centre principal point: K [x y 1]^T lands back on the pixel
+    K = np.array([[310.5, 0.7, 63.2], [0, 295.1, 40.9], [0, 0, 1.0]])
+    g = camera.Camera(80, 120, K, ray_from_pix_center=True)
+    uv = K @ g.homogeneous_coordinates.reshape(3, -1)
+    np.testing.assert_allclose(uv[0].reshape(80, 120)[5, 7], 7.5, atol=1e-9)
+    np.testing.assert_allclose(uv[1].reshape(80, 120)[5, 7], 5.5, atol=1e-9)
