@@ -109,6 +109,9 @@ class FrameGather:
         M, N, _, Ht, Wt = rgba.shape
         V = ray_dir.shape[0]
         assert V <= self.frames_per_rank and ray_dir.shape[2:] == (self.H, self.W)
+        for name, t in (("rgba", rgba), ("dhw", dhw), ("ray_dir", ray_dir), ("eye", eye), ("z_dir", z_dir)):   # raw pointers below
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), f"{name} must be a contiguous fp32 CUDA tensor"
+        assert view2mpi.dtype == torch.int32 and view2mpi.is_contiguous() and flags.dtype == torch.int32
         options = (_lib.OPT_ALIGN_CORNERS if align_corners else 0) | (_lib.OPT_CHECK_LAST_PLANE if check_last_plane else 0) \
             | (_lib.OPT_COLOR_MINUS1_1 if color_minus1_1 else 0)
         with torch.cuda.device(rgba.device):
