@@ -13,7 +13,6 @@ torch ops -- plumbing on small tensors.  With the generator's FACTORED output th
 
 No CPU path: tensors must live on a CUDA device.
 """
-import ctypes
 from typing import Optional
 
 import numpy as np

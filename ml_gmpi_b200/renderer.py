@@ -15,7 +15,6 @@ are built once and cached (the reference rebuilds 4^2 ... tex^2 on every `get_xy
 iteration, train.py:467,818), and the "disparity" option returns new tensors instead of inverting the cache in place.
 """
 import logging
-from typing import Optional
 
 import numpy as np
 import torch

@@ -58,7 +58,6 @@ def test_synth_case_shapes():
 
 def test_renderer_facade_constructor_matches_reference_table():
     from ml_gmpi_b200.renderer import MPIRenderer
-    from ml_gmpi_b200.geometry import FFHQ
     r = MPIRenderer(n_mpi_planes=8, plane_min_d=0.95, plane_max_d=1.12, plan_spatial_enlarge_factor=1.001,
                     plane_distances_sample_method="inverse", cam_fov=12.6, sphere_center_z=1.0, sphere_r=1.0,
                     horizontal_mean=0.0, horizontal_std=0.289, vertical_mean=0.0, vertical_std=0.127,
