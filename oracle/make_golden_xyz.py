@@ -46,6 +46,20 @@ def main():
     c2w = np.array([[0.96, 0.0, -0.28, 0.28], [0.0, 1.0, 0.0, 0.0], [0.28, 0.0, 0.96, 0.04], [0, 0, 0, 1]], np.float32)
     ray, eye, z_dir, tf = cam_r.view_info_from_c2w_mat(cam_r.cam, c2w)
     out["vi_c2w"], out["vi_ray"], out["vi_eye"], out["vi_z"], out["vi_tf"] = c2w, ray.numpy(), eye.numpy(), z_dir.numpy(), tf.numpy()
+    # seeded RANDOM poses: the mirror must consume torch's global RNG exactly as the reference does (cam_utils.py:510-555,
+    # torch_utils.py:51-76), so that a seeded training / FID run draws the same cameras
+    for method in ("truncated_gaussian", "uniform", "normal"):
+        kw = dict(ref_shim.FFHQ_KWARGS, cam_sample_method=method)
+        rr = ref_r.MPIRenderer(n_mpi_planes=4, device=torch.device("cpu"), **kw)
+        rr.set_cam(12.6, 8, 8)
+        torch.manual_seed(3)
+        y, p, c2w, *_ = rr.sample_cam_poses(5, 0.0, 0.289, 0.0, 0.127, True)
+        y2, p2, _c, *_ = rr.sample_cam_poses(3, 0.1, 0.2, -0.05, 0.1, True)          # second draw from the same stream
+        out[f"rand_{method}_yaw"], out[f"rand_{method}_pitch"] = y.numpy().copy(), p.numpy().copy()
+        out[f"rand_{method}_c2w"] = np.asarray(c2w.numpy() if isinstance(c2w, torch.Tensor) else c2w, np.float32)
+        out[f"rand_{method}_yaw2"], out[f"rand_{method}_pitch2"] = y2.numpy().copy(), p2.numpy().copy()
+    y, p, c2w, *_ = rr.sample_cam_poses(5, 0.1, 0.289, 0.05, 0.127, False)           # deterministic horizontal sweep
+    out["sweep_yaw"], out["sweep_pitch"] = y.numpy().copy(), p.numpy().copy()
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "ffhq_xyz.npz"), **out)
     print("wrote ffhq_xyz.npz:", {k: v.shape for k, v in out.items()})

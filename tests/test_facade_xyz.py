@@ -118,3 +118,27 @@ def test_facade_has_every_public_method_of_the_reference_with_its_signature():
             continue
         assert hasattr(MPIRenderer, name), f"MPIRenderer.{name} missing"
         assert params(getattr(MPIRenderer, name)) == params(fn), name
+
+
+@pytest.mark.parametrize("method", ["truncated_gaussian", "uniform", "normal"])
+def test_seeded_random_poses_equal_the_reference(method):
+    """Same torch seed -> the same cameras as the reference draws (RNG consumed in the same order and amounts:
+    cam_utils.py:510-555, torch_utils.py:51-76), also on the second call from the same stream."""
+    ref = load_golden("ffhq_xyz")
+    r = MPIRenderer(n_mpi_planes=4, **dict(KW, cam_sample_method=method))
+    r.set_cam(12.6, 8, 8)
+    torch.manual_seed(3)
+    y, p, c2w, rays, eyes, zs = r.sample_cam_poses(5, 0.0, 0.289, 0.0, 0.127, True)
+    assert np.array_equal(y.numpy(), ref[f"rand_{method}_yaw"]) and np.array_equal(p.numpy(), ref[f"rand_{method}_pitch"])
+    np.testing.assert_allclose(c2w.numpy(), ref[f"rand_{method}_c2w"], atol=2e-7)
+    assert len(rays) == 5 and rays[0].shape == (1, 3, 8, 8) and eyes[0].shape == (1, 3) and zs[0].shape == (1, 3)
+    y2, p2, *_ = r.sample_cam_poses(3, 0.1, 0.2, -0.05, 0.1, True)
+    assert np.array_equal(y2.numpy(), ref[f"rand_{method}_yaw2"]) and np.array_equal(p2.numpy(), ref[f"rand_{method}_pitch2"])
+
+
+def test_deterministic_sweep_equals_the_reference():
+    ref = load_golden("ffhq_xyz")
+    r = MPIRenderer(n_mpi_planes=4, **KW)
+    r.set_cam(12.6, 8, 8)
+    y, p, *_ = r.sample_cam_poses(5, 0.1, 0.289, 0.05, 0.127, False)
+    assert np.array_equal(y.numpy(), ref["sweep_yaw"]) and np.array_equal(p.numpy(), ref["sweep_pitch"])
