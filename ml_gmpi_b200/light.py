@@ -162,10 +162,18 @@ class LightRenderer:
     def compute_pcl(self, mpi_alpha, mpi_plane_dhws, mpi_tex_pix_xyz):
         plane_ds = mpi_plane_dhws[:, :1].to(mpi_alpha.device)
         mpi_depth = self.compute_depth(mpi_alpha, plane_ds)
-        mpi_depth = gaussian_blur(mpi_depth, self.blur_ksize, self.blur_sigma)[:, 0, ...]
+        mpi_depth = self._blur(mpi_depth)[:, 0, ...]
         mpi_xyz_last_plane = mpi_tex_pix_xyz[-1:, :, :, :3]
         scale = mpi_depth.unsqueeze(-1) / (mpi_xyz_last_plane[..., 2:] + EPS)
         return mpi_xyz_last_plane * scale
+
+    def _blur(self, img):
+        """The reference blurs with torchvision.transforms.GaussianBlur(sigma=(s, s)) (light_renderer.py:50-53,112), whose forward
+        draws its sigma with torch.empty(1).uniform_(s, s) -- ONE value of torch's global CPU generator per call, BEFORE the light is
+        sampled.  The draw is repeated here (its value is s whatever the generator returns) so that a seeded run sees the same
+        random stream -- the same lights, and the same poses and latents afterwards -- as with the reference."""
+        torch.empty(1).uniform_(self.blur_sigma, self.blur_sigma)
+        return gaussian_blur(img, self.blur_ksize, self.blur_sigma)
 
     def sample_light_directions(self, bs, device, given_yaws=None, given_pitches=None):
         """Light position on the camera sphere, direction towards its centre (light_renderer.py:136-165)."""

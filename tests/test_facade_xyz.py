@@ -142,3 +142,23 @@ def test_deterministic_sweep_equals_the_reference():
     r.set_cam(12.6, 8, 8)
     y, p, *_ = r.sample_cam_poses(5, 0.1, 0.289, 0.05, 0.127, False)
     assert np.array_equal(y.numpy(), ref["sweep_yaw"]) and np.array_equal(p.numpy(), ref["sweep_pitch"])
+
+
+def test_light_renderer_draws_the_reference_light_from_the_same_seed():
+    """LightRenderer.render blurs the depth (torchvision's GaussianBlur draws its sigma from torch's global generator: one
+    uniform per call) and then samples the light with gen_sphere_path (light_renderer.py:112,136-149);
+    tests/golden/light_2x6x32.npz recorded what the unmodified reference drew after torch.manual_seed(5).  The mirror must
+    consume the generator identically, or every later draw of a seeded training run (lights, poses, latents) would differ."""
+    from ml_gmpi_b200.light import LightRenderer, gaussian_blur
+    ref = load_golden("light_2x6x32")
+    lr = LightRenderer(sphere_center_z=1.0, sphere_r=1.0, ka_max=0.7, kd_max=0.6, n_grow_iters=10)
+    img = torch.rand(2, 1, 32, 32, generator=torch.Generator().manual_seed(1))
+    torch.manual_seed(5)
+    blurred = lr._blur(img)                                   # what compute_pcl runs before the light is sampled
+    assert torch.equal(blurred, gaussian_blur(img, lr.blur_ksize, lr.blur_sigma))
+    d = lr.sample_light_directions(2, torch.device("cpu"))
+    from ml_gmpi_b200.camera import sphere_poses
+    c2w = sphere_poses(torch.from_numpy(ref["light_yaws"]).reshape(2, 1), torch.from_numpy(ref["light_pitches"]).reshape(2, 1),
+                       (0, 0, 1.0), 1.0)
+    want = torch.tensor([[0.0, 0.0, 1.0]]) - c2w[:, :3, 3]
+    assert torch.equal(d, want / torch.norm(want, dim=-1, keepdim=True))

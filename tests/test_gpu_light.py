@@ -53,6 +53,18 @@ def test_render_matches_the_reference_shaded_mpi_and_gradient():
     assert rel_err(mpi.grad.cpu().numpy(), gd["g_mpi"]) <= 5e-5         # through clip mask, normals, blur and the depth composite
 
 
+def test_seeded_render_draws_the_reference_light():
+    """No given light: after torch.manual_seed(5) the mirror consumes the global generator like the reference (blur's sigma draw,
+    then the light's truncated normals), so the shaded MPI equals the reference's output for that seed."""
+    gd = load_golden("light_2x6x32")
+    d = dev()
+    t = lambda a: torch.from_numpy(a).to(d)
+    lr = make_lr()
+    torch.manual_seed(5)
+    out = lr.render(t(gd["mpi"]), t(gd["dhw"]), t(gd["xyz"]))
+    assert rel_err(out.cpu().numpy(), gd["out"]) <= 1e-5
+
+
 def test_factored_shading_equals_shading_the_expanded_stack():
     gd = load_golden("light_2x6x32")
     d = dev()
