@@ -100,3 +100,29 @@ def test_oracle_range_flags():
     assert mpi_oracle.check_range(bad) == mpi_oracle.FLAG_RGBA_RANGE
     bad = g["rgba"].copy(); bad[1, 2, 3, 3, 3] = -0.1
     assert mpi_oracle.check_range(bad) & mpi_oracle.FLAG_ALPHA_RANGE
+
+
+# Edge cases of the reference's forward that only the ORACLE is pinned with (oracle/make_golden_edge.py): a single plane, an MPI
+# without views between MPIs with views, align_corners=False on a non-square texture, sizes that are multiples of nothing.
+EDGE_CASES = ["edge_single_plane", "edge_ragged_zero_views", "edge_acfalse_nonsquare", "edge_odd_sizes"]
+
+
+@pytest.mark.parametrize("name", EDGE_CASES)
+def test_edge_cases_c_oracle_and_torch_port(name):
+    g = load_golden(name)
+    ac = bool(g["align_corners"])
+    color, depth, _ = mpi_oracle.forward(g["rgba"], g["view2mpi"], g["dhw"], g["ray_dir"], g["eye"], g["z_dir"],
+                                         align_corners=ac, check_last_plane=False, nthreads=2)
+    assert color.shape == g["color"].shape and rel_err(color, g["color"]) <= TOL and rel_err(depth, g["depth"]) <= TOL
+    gr = mpi_oracle.backward(g["rgba"], g["view2mpi"], g["dhw"], g["ray_dir"], g["eye"], g["z_dir"], g["g_color"], g.get("g_depth"),
+                             align_corners=ac)
+    assert rel_err(gr, g["g_rgba"]) <= 5e-6
+    c_over, d_over = mpi_oracle.forward_over(g["rgba"], g["view2mpi"], g["dhw"], g["ray_dir"], g["eye"], g["z_dir"], align_corners=ac)
+    assert rel_err(c_over, g["color_over"]) <= TOL and rel_err(d_over, g["depth_over"]) <= TOL
+    rays, eyes, zs = _groups(g)
+    pc, pd = torch_port.render_views(torch.from_numpy(g["rgba"]), torch.from_numpy(g["dhw"]), rays, eyes, zs, align_corners=ac)
+    assert np.array_equal(pc.numpy(), g["color"]) and np.array_equal(pd.numpy(), g["depth"])
+    if name == "edge_ragged_zero_views":
+        assert g["view2mpi"].tolist() == [0, 0, 2] and not gr[1].any()          # the view-less MPI gets an exactly zero gradient
+    if name == "edge_single_plane":                                             # N = 1: colour = alpha_0 * rgb_0 of the warped plane
+        assert g["rgba"].shape[1] == 1 and float(np.max(color)) <= 1.0
