@@ -10,6 +10,11 @@ and numpy conversions folded into batched launches -- SURVEY.md 8(f) row N4.
                         (img_counter = rank; += world_size), rendered from a random pose, converted like torchvision's
                         save_image(normalize=True, range=(-1, 1)) and written as f"{k:0>5}.png".
 
+  render_eval_views     `generate_img` of the evaluation-data dump (gmpi/eval/prepare_fake_data.py:17-95): every MPI of a batch from
+                        n_imgs random poses -- the reference expands the batch to B*n_imgs copies of the MPI before rendering
+                        (:59-64); here the views index their MPI (`view_group` = n_imgs orders the tiles for L2 reuse).  Returns
+                        the reference's triple: uint8 images (truncating conversion, :72-74), fp32 metric depth maps, (pitch, yaw).
+
 The MPI itself comes from the caller (`mpi_source`): the generator is outside the render path.  `render_fn` is injectable so
 that the sharding / ordering logic is testable without a GPU (tests/test_service.py); the default is the CUDA renderer.
 """
@@ -126,3 +131,38 @@ def dump_fid_images(renderer, mpi_source: Callable[[int], torch.Tensor], num_img
                 Image.fromarray(img).save(os.path.join(output_dir, f"{idx:0>5}.png"))
             done.append(idx)
     return done
+
+
+def to_uint8_truncating(img_m11: torch.Tensor) -> torch.Tensor:
+    """[-1,1] fp32 -> uint8 as prepare_fake_data.py:72-74 / render_video.py:119-121 convert: clip((x + 1) / 2, 0, 1) * 255,
+    truncated (numpy's astype(uint8)); the same fp32 operations, so the bytes are identical."""
+    return (torch.clamp((img_m11 + 1) / 2.0, 0.0, 1.0) * 255).to(torch.uint8)
+
+
+def _default_eval_render(renderer, batch_mpi, n_imgs, img_size, yaws, pitches):
+    from .mpi import render_frames
+    dev = batch_mpi.device
+    B = batch_mpi.shape[0]
+    c2w = sphere_poses(yaws, pitches, renderer.sphere_center, renderer.sphere_r).to(dev)
+    ray_dir, eye, z_dir = PinholeCamera.from_fov(renderer.cam_fov, img_size, img_size).generate_rays(c2w)
+    dhw = renderer.static_mpi_plane_dhws.to(dev).reshape(1, -1, 3).expand(B, -1, -1).contiguous()
+    view2mpi = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(n_imgs)
+    return render_frames(rgba=batch_mpi, dhw=dhw, view2mpi=view2mpi, ray_dir=ray_dir, eye=eye, z_dir=z_dir, check_last_plane=True,
+                         view_group=n_imgs)                              # (colour in [-1,1] [V,3,H,W], depth [V,1,H,W])
+
+
+def render_eval_views(renderer, batch_mpi: torch.Tensor, n_imgs: int, img_size: int, *, generator: Optional[torch.Generator] = None,
+                      render_fn: Optional[Callable] = None):
+    """batch_mpi [B,N,4,T,T] -> (img uint8 [B*n_imgs,H,W,3], depth fp32 [B*n_imgs,H,W,1], angles fp32 [B*n_imgs,2] = (pitch,
+    yaw)) as numpy arrays, views MPI-major (the n_imgs views of MPI 0 first) like the reference's expand.  Poses are drawn
+    as MPIRenderer.render draws them for a batch of B*n_imgs (same generator consumption: mpi_renderer.py:418-434)."""
+    B = batch_mpi.shape[0]
+    V = B * int(n_imgs)
+    yaws, pitches = sample_yaw_pitch(V, renderer.horizontal_mean, renderer.horizontal_std, renderer.vertical_mean, renderer.vertical_std,
+                                     renderer.cam_pose_n_truncated_stds, renderer.cam_sample_method, True, generator=generator)
+    fn = render_fn or _default_eval_render
+    img, depth = fn(renderer, batch_mpi, int(n_imgs), img_size, yaws, pitches)
+    assert img.shape[0] == V and depth.shape[0] == V, f"{img.shape}, {depth.shape}, {V}"
+    img_u8 = to_uint8_truncating(img.permute(0, 2, 3, 1)).cpu().numpy()
+    angles = torch.cat([pitches, yaws], dim=-1).numpy()                 # mpi_renderer.py:464
+    return img_u8, depth.permute(0, 2, 3, 1).float().cpu().numpy(), angles
