@@ -188,6 +188,15 @@ def cpu_reference_frames_per_s(steps, warmup, budget_s, planes=N_PLANES, res=RES
     return {"value": 1.0 / t, "sample": sample, "cores": cores, "ms_per_step": t * 1e3, "spread": spread}
 
 
+def headline_config(NP, R, B, world):
+    """`config` of the JSON line: the workload only, so that both arms (`--impl reference` included) print the same object."""
+    default = (NP, R, B) == (N_PLANES, RES, BATCH)
+    return {"workload": WORKLOAD if default else f"{NP} planes, {R}^2, {B} MPIs x 1 view per GPU, forward render",
+            "planes": NP, "tex": R, "img": R, "mpis_per_gpu": B, "views_per_gpu": B,
+            "parallelism": f"views sharded x{world}: every GPU renders its own {B} MPIs x 1 view; one all-gather of frames per step when x > 1",
+            "l2": f"inputs {B * NP * 4 * R * R * 4 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)"}
+
+
 def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -198,7 +207,7 @@ def run_reference_arm(args, out):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "planes": N_PLANES, "tex": RES, "img": RES, "device": "host CPU"},
+        "config": headline_config(N_PLANES, RES, BATCH, args.gpus), "device": "host CPU",
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                          "spread": r["spread"], "stable": r["spread"] < 0.2},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -899,7 +908,6 @@ def _main(argv, out):
     e2e = None
     if not args.no_e2e:
         e2e = leg_e2e(job, state, max(2, min(args.steps, 4)), B)
-    l2_note = f"inputs {state['case'].rgba.numel() * 4 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)"
     state = None
     if be.name == "cuda":
         be.torch.cuda.empty_cache()
@@ -921,10 +929,8 @@ def _main(argv, out):
             "metric": METRIC, "value": head["frames_per_s"], "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (NP, R, B) == (N_PLANES, RES, BATCH) else f"{NP} planes, {R}^2, {B} MPIs x 1 view per GPU",
-                       "planes": NP, "tex": R, "img": R, "mpis_per_gpu": B, "views_per_gpu": B,
-                       "parallelism": f"views sharded x{world}; all-gather of frames: {head['gather_mode']}", "l2": l2_note,
-                       "validate": "geometric flags fused in-kernel; range scan off in the timed region"},
+            "config": headline_config(NP, R, B, world), "collective": f"all-gather of frames: {head['gather_mode']}",
+            "validate": "geometric flags fused in-kernel; range scan off in the timed region",
             "clocks": head["clocks"], "e2e": e2e, "gpu_launches": head["launches"], "roofline": head["roofline"], "cpu_baseline": cpu,
             "train_step": train, "configs": configs, "reference_on_gpu": ref_gpu,
         }

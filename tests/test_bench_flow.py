@@ -47,7 +47,8 @@ def test_default_command_line_runs_every_leg(world, no_symm):
     assert line["e2e"]["matches_device_resident_run"] and line["e2e"]["h2d_bytes_per_step"] > 0
     assert set(line["configs"]) >= {"C2_ffhq256_fwd", "N1_factored_fwd", "C4_video_512", "C5_train_512"}
     assert line["configs"]["C4_video_512"]["scaling"] == "strong"
-    par = line["config"]["parallelism"]
+    assert f"x{world}" in line["config"]["parallelism"] and "L2" in line["config"]["l2"]
+    par = line["collective"]
     if world == 1:
         assert "none" in par
     elif no_symm:
@@ -67,3 +68,25 @@ def test_usable_cores_respects_affinity():
     import bench
     n = bench.usable_cores()
     assert 1 <= n <= len(os.sched_getaffinity(0))
+
+
+def test_reference_arm_prints_the_product_arms_config(monkeypatch, capsys):
+    """`--impl reference` runs on the product arm's `config` (same object), so the driver can pair the two lines."""
+    import argparse
+    import bench
+    monkeypatch.setattr(bench, "cpu_reference_frames_per_s", lambda steps, warmup, budget_s=0: {
+        "value": 0.5, "sample": "stub", "cores": 3, "ms_per_step": 2000.0, "spread": 0.0})
+    monkeypatch.setenv("RANK", "0")
+
+    class Out:
+        lines = []
+
+        def emit(self, s):
+            self.lines.append(s)
+
+    bench.run_reference_arm(argparse.Namespace(steps=2, warmup=1, gpus=4, ref_budget_s=1.0), Out())
+    line = json.loads(Out.lines[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 4 and line["cpu_baseline"]["cores"] == 3
+    assert line["config"] == bench.headline_config(bench.N_PLANES, bench.RES, bench.BATCH, 4)
+    assert line["e2e"] == {"value": 0.5, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["metric"] == bench.METRIC and line["unit"] == "frames/s" and line["higher_is_better"] is True
